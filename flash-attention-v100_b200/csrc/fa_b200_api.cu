@@ -1,0 +1,423 @@
+// libfa_b200.so: the C ABI declared in include/fa_b200.h.
+//
+// Host side of the forward hot path: argument validation and the normalisations the reference does
+// in its C++ wrappers (kernel/fused_mha_forward.cu:301-432, kernel/fused_mha_forward_varlen.cu:
+// 371-566, kernel/fused_mha_forward_kvcache.cu:416-652), TMA tensor-map encoding, and the launches.
+// No torch / ATen types, no device allocation, no stream synchronisation.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/fa_b200.h"
+#include "fwd_sm100.cuh"
+#include "kvcache_prep.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+}
+#define CHECK_ARG(cond, ...) \
+    do {                     \
+        if (!(cond)) return fail(FA_B200_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+// 4-D view (head_dim, heads, rows, batch) of a 16-bit tensor with unit head_dim stride;
+// box = 64 x 1 x 128 x 1 with the 128-byte swizzle the UMMA descriptors expect.
+int make_tmap(CUtensorMap* tm, int dtype, const void* ptr, int head_dim, int64_t heads, int64_t rows,
+              int64_t batch, int64_t stride_h, int64_t stride_s, int64_t stride_b, const char* name) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(FA_B200_EARCH, "cuTensorMapEncodeTiled is not available from this driver");
+    CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s must be 16-byte aligned", name);
+    CHECK_ARG(stride_h % 8 == 0 && stride_s % 8 == 0 && stride_b % 8 == 0,
+              "%s strides must be multiples of 8 elements (16 bytes)", name);
+    cuuint64_t dims[4] = {(cuuint64_t)head_dim, (cuuint64_t)(heads > 0 ? heads : 1), (cuuint64_t)(rows > 0 ? rows : 1),
+                          (cuuint64_t)(batch > 0 ? batch : 1)};
+    auto nz = [](int64_t s) { return (cuuint64_t)((s > 0 ? s : 8) * 2); };
+    cuuint64_t strides[3] = {nz(stride_h), nz(stride_s), nz(stride_b)};
+    cuuint32_t box[4] = {64, 1, 128, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, dtype == FA_B200_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                     4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FA_B200_EINVAL, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", name, (int)r);
+    return 0;
+}
+
+int check_device(int device) {
+    static int cached_major[64];
+    static bool cached[64];
+    if (device < 0 || device >= 64) return fail(FA_B200_EINVAL, "bad device ordinal %d", device);
+    if (!cached[device]) {
+        int major = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+        cached_major[device] = major;
+        cached[device] = true;
+    }
+    if (cached_major[device] != 10)
+        return fail(FA_B200_EARCH, "this library only runs on sm_100 (B200); device %d is sm_%dx", device, cached_major[device]);
+    return 0;
+}
+
+template <int D, bool BF16, bool FEAT>
+int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+    using Cfg = fa::FwdConfig<D>;
+    auto kern = fa::fa_fwd_sm100_kernel<D, BF16, FEAT>;
+    static std::once_flag once[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t attr_err = cudaSuccess;
+    std::call_once(once[dev & 63], [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    });
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(smem)");
+    kern<<<grid, 512, Cfg::kSmemBytes, stream>>>(kp);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fa_fwd_sm100_kernel launch");
+    return 0;
+}
+
+int launch_fwd(const fa::FwdKernelParams& kp, int head_dim, int dtype, bool feat, dim3 grid, cudaStream_t stream) {
+    const bool bf16 = dtype == FA_B200_DTYPE_BF16;
+#define FA_CASE(DD, BB, FF) \
+    if (head_dim == DD && bf16 == BB && feat == FF) return launch_fwd_t<DD, BB, FF>(kp, grid, stream);
+    FA_CASE(128, true, false)
+    FA_CASE(128, true, true)
+    FA_CASE(128, false, false)
+    FA_CASE(128, false, true)
+    FA_CASE(64, true, false)
+    FA_CASE(64, true, true)
+    FA_CASE(64, false, false)
+    FA_CASE(64, false, true)
+#undef FA_CASE
+    return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (64 and 128 are)", head_dim);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int check_common(const fa_b200_params_t* p) {
+    if (!p) return fail(FA_B200_EINVAL, "params is NULL");
+    CHECK_ARG(p->struct_bytes == (int32_t)sizeof(fa_b200_params_t),
+              "fa_b200_params_t size mismatch: caller %d, library %d (ABI %d)", p->struct_bytes,
+              (int)sizeof(fa_b200_params_t), FA_B200_ABI_VERSION);
+    CHECK_ARG(p->dtype == FA_B200_DTYPE_FP16 || p->dtype == FA_B200_DTYPE_BF16, "dtype must be fp16 (0) or bf16 (1)");
+    CHECK_ARG(p->batch > 0, "batch size must be positive");
+    CHECK_ARG(p->num_heads > 0 && p->num_heads_k > 0, "head counts must be positive");
+    CHECK_ARG(p->num_heads % p->num_heads_k == 0, "H_Q must be divisible by H_K for GQA/MQA");
+    CHECK_ARG(p->head_dim % 8 == 0, "head dimension must be multiple of 8");
+    CHECK_ARG(p->head_dim <= 256, "head dimension must be <= 256");
+    if (p->head_dim != 64 && p->head_dim != 128)
+        return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (64 and 128 are; the Python layer pads smaller dims)", p->head_dim);
+    CHECK_ARG(p->q && p->k && p->v && p->out && p->lse, "q, k, v, out and lse must be non-NULL");
+    CHECK_ARG(p->softcap >= 0.f, "softcap must be >= 0");
+    CHECK_ARG((reinterpret_cast<uintptr_t>(p->out) & 15) == 0 && p->o_stride_b % 8 == 0 && p->o_stride_s % 8 == 0 &&
+                  p->o_stride_h % 8 == 0,
+              "out must be 16-byte aligned with strides that are multiples of 8 elements");
+    return check_device(p->device);
+}
+
+void fill_common(fa::FwdKernelParams& kp, const fa_b200_params_t* p, bool causal, int wl, int wr) {
+    memset(&kp, 0, sizeof(kp));
+    kp.out = p->out;
+    kp.lse = p->lse;
+    kp.o_stride_b = p->o_stride_b;
+    kp.o_stride_s = p->o_stride_s;
+    kp.o_stride_h = p->o_stride_h;
+    kp.alibi = p->alibi_slopes;
+    kp.alibi_stride_b = p->alibi_stride_b;
+    kp.num_heads = p->num_heads;
+    kp.heads_per_kv = p->num_heads / p->num_heads_k;
+    kp.scale = p->softmax_scale;
+    kp.scale_log2 = p->softmax_scale * fa::kLog2e;
+    kp.softcap = p->softcap;
+    kp.window_left = wl;
+    kp.window_right = causal ? 0 : wr;  // the causal mask is the right window of width 0
+    kp.reverse_m = (kp.window_right >= 0 || kp.window_left >= 0) ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+FA_B200_API int fa_b200_abi_version(void) { return FA_B200_ABI_VERSION; }
+FA_B200_API const char* fa_b200_last_error(void) { return g_err; }
+FA_B200_API int64_t fa_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+FA_B200_API int64_t fa_b200_workspace_bytes(const fa_b200_params_t* p, int kind) {
+    if (!p || kind != FA_B200_KIND_KVCACHE) return 0;
+    int64_t bytes = 0;
+    if (p->rotary_dim > 0)  // rotated copy of q
+        bytes += (int64_t)p->batch * p->seqlen_q * p->num_heads * p->head_dim * 2;
+    bytes = (bytes + 255) & ~(int64_t)255;
+    return bytes;
+}
+
+// ------------------------------------------------------------------------------------------ dense
+FA_B200_API int fa_b200_fwd(const fa_b200_params_t* p, void* stream_v) {
+    g_err[0] = 0;
+    if (int rc = check_common(p)) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    CHECK_ARG(p->seqlen_q > 0, "seqlen_q must be positive");
+    CHECK_ARG(p->seqlen_k > 0, "seqlen_k must be positive (the caller handles the empty-KV case)");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(FA_B200_EINVAL, "cannot select device %d", p->device);
+
+    // reference kernel/fused_mha_forward.cu:343,351-352
+    bool causal = p->is_causal != 0;
+    if (p->seqlen_q == 1 && !p->alibi_slopes) causal = false;
+    int wl = p->window_left, wr = p->window_right;
+    if (wl >= p->seqlen_k) wl = -1;
+    if (wr >= p->seqlen_k) wr = -1;
+
+    fa::FwdKernelParams kp;
+    fill_common(kp, p, causal, wl, wr);
+    kp.seqlen_q = p->seqlen_q;
+    kp.seqlen_k = p->seqlen_k;
+    kp.lse_stride_b = (int64_t)p->num_heads * p->seqlen_q;
+    kp.lse_stride_h = p->seqlen_q;
+    if (int rc = make_tmap(&kp.tm_q, p->dtype, p->q, p->head_dim, p->num_heads, p->seqlen_q, p->batch, p->q_stride_h, p->q_stride_s, p->q_stride_b, "q")) return rc;
+    if (int rc = make_tmap(&kp.tm_k, p->dtype, p->k, p->head_dim, p->num_heads_k, p->seqlen_k, p->batch, p->k_stride_h, p->k_stride_s, p->k_stride_b, "k")) return rc;
+    if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, p->seqlen_k, p->batch, p->v_stride_h, p->v_stride_s, p->v_stride_b, "v")) return rc;
+
+    const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
+    dim3 grid((p->seqlen_q + 255) / 256, p->num_heads, p->batch);
+    return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
+}
+
+// ------------------------------------------------------------------------------------------ varlen
+FA_B200_API int fa_b200_varlen_fwd(const fa_b200_params_t* p, void* stream_v) {
+    g_err[0] = 0;
+    if (int rc = check_common(p)) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    CHECK_ARG(p->cu_seqlens_q && p->cu_seqlens_k, "cu_seqlens_q and cu_seqlens_k are required");
+    CHECK_ARG(p->total_q > 0, "total_q must be positive");
+    CHECK_ARG(p->seqlen_q > 0 && p->seqlen_k > 0, "max_seqlen_q / max_seqlen_k must be positive");
+    CHECK_ARG(p->num_splits <= 1, "num_splits > 1 is not supported");  // reference ..._varlen.cu:422
+    const bool paged = p->block_table != nullptr;
+    if (paged) {
+        CHECK_ARG(p->page_size > 0 && p->page_size % 128 == 0, "page_block_size must be a multiple of 128");
+        CHECK_ARG(p->num_pages > 0, "num_pages must be positive for paged KV");
+    } else {
+        CHECK_ARG(p->total_k > 0, "total_k must be positive");
+    }
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(FA_B200_EINVAL, "cannot select device %d", p->device);
+
+    // reference kernel/fused_mha_forward_varlen.cu:425, 481-482
+    bool causal = p->is_causal != 0;
+    if (p->seqlen_q == 1 && !p->alibi_slopes) causal = false;
+    int wl = p->window_left, wr = p->window_right;
+    if (wl >= p->seqlen_k) wl = -1;
+    if (wr >= p->seqlen_k) wr = -1;
+
+    fa::FwdKernelParams kp;
+    fill_common(kp, p, causal, wl, wr);
+    kp.seqlen_q = p->seqlen_q;
+    kp.seqlen_k = p->seqlen_k;
+    kp.cu_seqlens_q = p->cu_seqlens_q;
+    kp.cu_seqlens_k = p->cu_seqlens_k;
+    kp.seqused_k = p->seqused_k;
+    kp.block_table = p->block_table;
+    kp.block_table_stride = p->block_table_stride;
+    kp.page_size = p->page_size;
+    kp.lse_stride_b = 0;  // lse is [H, total_q] (reference ..._varlen.cu:519)
+    kp.lse_stride_h = p->total_q;
+    if (int rc = make_tmap(&kp.tm_q, p->dtype, p->q, p->head_dim, p->num_heads, p->total_q, 1, p->q_stride_h, p->q_stride_s, 0, "q")) return rc;
+    if (paged) {
+        if (int rc = make_tmap(&kp.tm_k, p->dtype, p->k, p->head_dim, p->num_heads_k, p->page_size, p->num_pages, p->k_stride_h, p->k_stride_s, p->k_stride_b, "k")) return rc;
+        if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, p->page_size, p->num_pages, p->v_stride_h, p->v_stride_s, p->v_stride_b, "v")) return rc;
+    } else {
+        if (int rc = make_tmap(&kp.tm_k, p->dtype, p->k, p->head_dim, p->num_heads_k, p->total_k, 1, p->k_stride_h, p->k_stride_s, 0, "k")) return rc;
+        if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, p->total_k, 1, p->v_stride_h, p->v_stride_s, 0, "v")) return rc;
+    }
+    const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
+    dim3 grid((p->seqlen_q + 255) / 256, p->num_heads, p->batch);
+    return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
+}
+
+// ------------------------------------------------------------------------------------------ kv-cache
+FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
+    g_err[0] = 0;
+    if (int rc = check_common(p)) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    CHECK_ARG(p->seqlen_q > 0, "seqlen_q must be positive");
+    CHECK_ARG(p->seqlen_k > 0, "cache capacity (seqlen_k) must be positive");
+    const bool paged = p->block_table != nullptr;
+    const bool has_new = p->k_new != nullptr;
+    const bool rotary = p->rotary_dim > 0;
+    // reference kernel/fused_mha_forward_kvcache.cu:469-472, 480, 506-509, 556, 569-594
+    CHECK_ARG((p->k_new != nullptr) == (p->v_new != nullptr), "k and v must be given together");
+    CHECK_ARG(!has_new || p->cache_seqlens, "cache_seqlens is required when k/v are appended");
+    CHECK_ARG(!has_new || p->seqlen_new > 0, "seqlen_new must be positive when k/v are appended");
+    if (p->softcap > 0.f) {
+        CHECK_ARG(p->window_left < 0 && p->window_right < 0, "softcap does not support a sliding window in the kv-cache path");
+        CHECK_ARG(!p->alibi_slopes, "softcap does not support ALiBi in the kv-cache path");
+    }
+    if (paged) {
+        CHECK_ARG(!p->cache_batch_idx, "paged KV does not support cache_batch_idx");
+        CHECK_ARG(!p->cache_leftpad, "paged KV does not support cache_leftpad");
+        CHECK_ARG(p->page_size > 0 && p->page_size % 128 == 0, "page_block_size must be a multiple of 128");
+        CHECK_ARG(p->num_pages > 0, "num_pages must be positive for paged KV");
+    } else {
+        CHECK_ARG(p->batch_k > 0, "batch_k (cache batch size) must be positive");
+    }
+    if (rotary) {
+        CHECK_ARG(has_new, "rotary embedding requires k/v to append");
+        CHECK_ARG(p->rotary_cos && p->rotary_sin, "rotary_cos and rotary_sin must both be given");
+        CHECK_ARG(p->rotary_dim <= p->head_dim, "rotary_dim must be <= head_dim");
+        CHECK_ARG(p->rotary_dim % 16 == 0, "rotary_dim must be a multiple of 16");
+        CHECK_ARG(p->rotary_seqlen >= p->seqlen_k, "rotary cos/sin must cover the cache length");
+        CHECK_ARG(p->workspace, "workspace is required when rotary is used (see fa_b200_workspace_bytes)");
+    }
+    CHECK_ARG(p->num_splits >= 0, "num_splits must be >= 0");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(FA_B200_EINVAL, "cannot select device %d", p->device);
+
+    // reference ..._kvcache.cu:465-466, 597-598
+    bool causal = p->is_causal != 0;
+    if (p->seqlen_q == 1 && !p->alibi_slopes) causal = false;
+    int wl = p->window_left, wr = p->window_right;
+    if (causal) wr = 0;
+    if (wl >= p->seqlen_k) wl = -1;
+    if (wr >= p->seqlen_k) wr = -1;
+    const bool bf16 = p->dtype == FA_B200_DTYPE_BF16;
+
+    // 1. append (+ RoPE on K), once per kv head
+    if (has_new) {
+        fa::AppendParams ap;
+        memset(&ap, 0, sizeof(ap));
+        ap.k_new = static_cast<const uint16_t*>(p->k_new);
+        ap.v_new = static_cast<const uint16_t*>(p->v_new);
+        ap.k_cache = static_cast<uint16_t*>(const_cast<void*>(p->k));
+        ap.v_cache = static_cast<uint16_t*>(const_cast<void*>(p->v));
+        ap.cos = static_cast<const uint16_t*>(p->rotary_cos);
+        ap.sin = static_cast<const uint16_t*>(p->rotary_sin);
+        ap.cache_seqlens = p->cache_seqlens;
+        ap.cache_batch_idx = p->cache_batch_idx;
+        ap.leftpad = p->cache_leftpad;
+        ap.block_table = p->block_table;
+        ap.knew_sb = p->knew_stride_b; ap.knew_ss = p->knew_stride_s; ap.knew_sh = p->knew_stride_h;
+        ap.vnew_sb = p->vnew_stride_b; ap.vnew_ss = p->vnew_stride_s; ap.vnew_sh = p->vnew_stride_h;
+        ap.kc_sb = p->k_stride_b; ap.kc_ss = p->k_stride_s; ap.kc_sh = p->k_stride_h;
+        ap.vc_sb = p->v_stride_b; ap.vc_ss = p->v_stride_s; ap.vc_sh = p->v_stride_h;
+        ap.batch = p->batch; ap.seqlen_new = p->seqlen_new; ap.heads_k = p->num_heads_k; ap.head_dim = p->head_dim;
+        ap.rotary_dim = rotary ? p->rotary_dim : 0;
+        ap.interleaved = p->rotary_interleaved;
+        ap.block_table_stride = p->block_table_stride;
+        ap.page_size = p->page_size;
+        const int64_t total = (int64_t)p->batch * p->seqlen_new * p->num_heads_k * (p->head_dim / 8);
+        const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+        if (bf16) fa::kv_append_kernel<true><<<blocks, 256, 0, stream>>>(ap);
+        else fa::kv_append_kernel<false><<<blocks, 256, 0, stream>>>(ap);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "kv_append_kernel launch");
+    }
+
+    // 2. RoPE on Q into the workspace
+    const void* q_ptr = p->q;
+    int64_t q_sb = p->q_stride_b, q_ss = p->q_stride_s, q_sh = p->q_stride_h;
+    char* ws = static_cast<char*>(p->workspace);
+    int64_t ws_left = p->workspace_bytes;
+    if (rotary) {
+        const int64_t qbytes = (((int64_t)p->batch * p->seqlen_q * p->num_heads * p->head_dim * 2) + 255) & ~(int64_t)255;
+        CHECK_ARG(ws_left >= qbytes, "workspace too small for the rotated q (%lld < %lld)", (long long)ws_left, (long long)qbytes);
+        fa::QRotaryParams rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.q = static_cast<const uint16_t*>(p->q);
+        rp.q_out = reinterpret_cast<uint16_t*>(ws);
+        rp.cos = static_cast<const uint16_t*>(p->rotary_cos);
+        rp.sin = static_cast<const uint16_t*>(p->rotary_sin);
+        rp.cache_seqlens = p->cache_seqlens;
+        rp.leftpad = p->cache_leftpad;
+        rp.q_sb = q_sb; rp.q_ss = q_ss; rp.q_sh = q_sh;
+        rp.batch = p->batch; rp.seqlen_q = p->seqlen_q; rp.heads = p->num_heads; rp.head_dim = p->head_dim;
+        rp.rotary_dim = p->rotary_dim;
+        rp.interleaved = p->rotary_interleaved;
+        rp.per_row_pos = (causal || wl >= 0 || wr >= 0) ? 1 : 0;
+        const int64_t total = (int64_t)p->batch * p->seqlen_q * p->num_heads * (p->head_dim / 8);
+        const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+        if (bf16) fa::q_rotary_kernel<true><<<blocks, 256, 0, stream>>>(rp);
+        else fa::q_rotary_kernel<false><<<blocks, 256, 0, stream>>>(rp);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "q_rotary_kernel launch");
+        q_ptr = ws;
+        q_sh = p->head_dim;
+        q_ss = (int64_t)p->num_heads * p->head_dim;
+        q_sb = (int64_t)p->seqlen_q * q_ss;
+        ws += qbytes;
+        ws_left -= qbytes;
+    }
+
+    // 3. attention over the cache: the tcgen05 kernel reading the (paged) cache through TMA
+    fa::FwdKernelParams kp;
+    fill_common(kp, p, causal, wl, wr);
+    kp.seqlen_q = p->seqlen_q;
+    kp.seqlen_k = p->seqlen_k;
+    kp.cache_seqlens = p->cache_seqlens;
+    kp.seqlen_k_add = has_new ? p->seqlen_new : 0;
+    kp.cache_batch_idx = p->cache_batch_idx;
+    kp.leftpad_k = p->cache_leftpad;
+    kp.block_table = p->block_table;
+    kp.block_table_stride = p->block_table_stride;
+    kp.page_size = p->page_size;
+    kp.lse_stride_b = (int64_t)p->num_heads * p->seqlen_q;
+    kp.lse_stride_h = p->seqlen_q;
+    if (int rc = make_tmap(&kp.tm_q, p->dtype, q_ptr, p->head_dim, p->num_heads, p->seqlen_q, p->batch, q_sh, q_ss, q_sb, "q")) return rc;
+    const int64_t rows = paged ? p->page_size : p->seqlen_k;
+    const int64_t nb = paged ? p->num_pages : p->batch_k;
+    if (int rc = make_tmap(&kp.tm_k, p->dtype, p->k, p->head_dim, p->num_heads_k, rows, nb, p->k_stride_h, p->k_stride_s, p->k_stride_b, "k_cache")) return rc;
+    if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, rows, nb, p->v_stride_h, p->v_stride_s, p->v_stride_b, "v_cache")) return rc;
+    const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
+    dim3 grid((p->seqlen_q + 255) / 256, p->num_heads, p->batch);
+    return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
+}
+
+}  // extern "C"

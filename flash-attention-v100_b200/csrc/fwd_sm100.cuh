@@ -1,0 +1,528 @@
+// Fused attention forward for sm_100a:  O = softmax(Q K^T * scale [+mask/bias/softcap]) V,  LSE.
+//
+// What it replaces: the reference's three forward kernels
+//   flash_attention_forward_kernel          (reference kernel/fused_mha_forward.cu:25-224)
+//   flash_attention_forward_varlen_kernel   (reference kernel/fused_mha_forward_varlen.cu:25-275)
+//   flash_attention_kvcache_kernel, Sq > 1  (reference kernel/fused_mha_forward_kvcache.cu:24-295)
+// and the per-tile building blocks they include (tile bounds include/template.h:36-112, score
+// modifiers include/mat_mul.h:82-157, online softmax include/softmax.h:21-203, epilogue
+// include/gemm_smem.h:119-205). Only the semantics are shared; the schedule is Blackwell-native:
+//
+//   * one CTA = 2 query tiles of 128 rows ("stages") x one (batch, head); KV streamed in 128-row tiles
+//   * warp 13 : TMA producer  (Q once, then K/V tiles into a ring of 128B-swizzled smem slots)
+//   * warp 12 : tcgen05.mma issuer.  S_s = Q_s K^T (SS form), O_s += P_s V (TS form, P read from
+//               TMEM, V consumed as the MN-major B operand).  Accumulators never leave TMEM.
+//   * warps 0-3 / 4-7 : softmax for stage 0 / 1.  thread == row (tcgen05.ld 32x32b), so the row
+//               max / row sum are thread-local; P is written back over S in TMEM as 16-bit pairs.
+//   * warps 8-11 : correction (lazy rescale of O in TMEM when the running max moved by > 2^8)
+//               and the epilogue (O / l -> 16-bit -> global, LSE).
+//   * everything is ordered with mbarriers; tcgen05.commit signals MMA completion.
+//
+// TMEM map (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D);
+// P_s aliases columns [64,128) of S_s (128 x 128 16-bit values = 64 columns).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+
+#include "ptx_sm100.cuh"
+
+namespace fa {
+
+struct alignas(64) FwdKernelParams {
+    CUtensorMap tm_q;  // 4-D (head_dim, heads, rows, batch), box (64, 1, 128, 1), 128B swizzle
+    CUtensorMap tm_k;
+    CUtensorMap tm_v;
+    void* out;
+    float* lse;
+    int64_t o_stride_b, o_stride_s, o_stride_h;  // elements
+    int64_t lse_stride_b, lse_stride_h;          // elements; row stride is 1
+    const int* cu_seqlens_q;
+    const int* cu_seqlens_k;
+    const int* seqused_k;
+    const int* cache_seqlens;
+    const int* cache_batch_idx;
+    const int* leftpad_k;
+    const int* block_table;
+    const float* alibi;
+    int64_t alibi_stride_b;
+    int block_table_stride;
+    int page_size;
+    int seqlen_q;
+    int seqlen_k;
+    int seqlen_k_add;  // rows appended to the cache before this call (kvcache)
+    int num_heads;
+    int heads_per_kv;
+    float scale;
+    float scale_log2;
+    float softcap;
+    int window_left;   // -1 = unbounded
+    int window_right;  // -1 = unbounded; causal is window_right = 0
+    int reverse_m;     // launch the longest query blocks first (causal / local)
+};
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kNegSentinel = -1e30f;  // reference NEG_INF (include/kernel.h:20) as the "no keys" LSE
+constexpr float kRescaleThreshold = 8.0f;  // log2 units; O is rescaled only when the max moves more
+
+template <int D>
+struct FwdConfig {
+    static constexpr int kBlockM = 128;
+    static constexpr int kBlockN = 128;
+    static constexpr int kTileBytes = kBlockN * D * 2;
+    static constexpr int kHalfBytes = kBlockN * 128;  // one 64-column (128-byte) swizzle block
+    static constexpr int kKvStages = (D == 128) ? 4 : 6;
+    static constexpr int kSmemQ = 2 * kTileBytes;
+    static constexpr int kSmemKV = kKvStages * kTileBytes;
+    static constexpr int kNumBars = 2 + 2 * kKvStages + 2 + 2 + 2 + 2 + 2;
+    static constexpr int kOffBars = kSmemQ + kSmemKV;
+    static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
+    static constexpr int kOffScale = (kOffTmemPtr + 16 + 15) & ~15;
+    static constexpr int kOffRowSum = kOffScale + 2 * 128 * 4;
+    static constexpr int kOffRowMax = kOffRowSum + 2 * 128 * 4;
+    static constexpr int kSmemUsed = kOffRowMax + 2 * 128 * 4;
+    static constexpr int kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
+    static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
+    static constexpr int kTmemPOff = 64;
+};
+
+// Per-sequence geometry shared by every role.
+struct SeqGeom {
+    int q_off, q_b, seqlen_q;
+    int k_off, k_b, seqlen_k;
+};
+
+FA_DEVICE SeqGeom load_geom(const FwdKernelParams& p, int batch) {
+    SeqGeom g;
+    g.q_off = 0;
+    g.q_b = batch;
+    g.seqlen_q = p.seqlen_q;
+    g.k_off = 0;
+    g.k_b = batch;
+    g.seqlen_k = p.seqlen_k;
+    if (p.cu_seqlens_q) {
+        g.q_off = p.cu_seqlens_q[batch];
+        g.seqlen_q = p.cu_seqlens_q[batch + 1] - g.q_off;
+        g.q_b = 0;
+    }
+    if (p.cu_seqlens_k) {
+        const int s = p.cu_seqlens_k[batch];
+        g.seqlen_k = p.cu_seqlens_k[batch + 1] - s;
+        if (!p.block_table) {
+            g.k_off = s;
+            g.k_b = 0;
+        }
+    }
+    if (p.cache_seqlens) g.seqlen_k = p.cache_seqlens[batch] + p.seqlen_k_add;
+    if (p.seqused_k) {  // reference include/template.h:65-68: used > 0 ? min(len, used) : 0
+        const int u = p.seqused_k[batch];
+        g.seqlen_k = u > 0 ? min(g.seqlen_k, u) : 0;
+    }
+    if (p.cache_batch_idx) g.k_b = p.cache_batch_idx[batch];
+    if (p.leftpad_k) g.k_off += p.leftpad_k[batch];
+    return g;
+}
+
+template <int D, bool BF16, bool FEAT>
+__global__ void __launch_bounds__(512, 1)
+fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
+    using Cfg = FwdConfig<D>;
+    constexpr int BM = Cfg::kBlockM, BN = Cfg::kBlockN;
+    constexpr int KV = Cfg::kKvStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_raw_u32 = smem_u32(smem_raw);
+    const uint32_t sbase = (smem_raw_u32 + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_raw_u32);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int m_block = p.reverse_m ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const int head = blockIdx.y;
+    const int batch = blockIdx.z;
+    const SeqGeom g = load_geom(p, batch);
+    const int m0 = m_block * (2 * BM);
+    if (m0 >= g.seqlen_q) return;  // over-provisioned varlen grid
+
+    // KV tile range [n_min, n_max) visible to this 256-row query block (bottom-right aligned).
+    const int off = g.seqlen_k - g.seqlen_q;
+    int n_max = (g.seqlen_k + BN - 1) / BN;
+    if (p.window_right >= 0) {
+        const int last_row = min(m0 + 2 * BM, g.seqlen_q) - 1;
+        const int max_col = last_row + off + p.window_right;
+        n_max = min(n_max, max_col < 0 ? 0 : max_col / BN + 1);
+    }
+    int n_min = 0;
+    if (p.window_left >= 0) {
+        const int min_col = m0 + off - p.window_left;
+        n_min = max(0, min_col >= 0 ? min_col / BN : 0);
+    }
+    const int n_tiles = n_max - n_min;
+    const int o_b = p.cu_seqlens_q ? 0 : batch;
+
+    if (n_tiles <= 0) {
+        // No visible key for any row of this block: out = 0, lse = sentinel
+        // (reference kernel/fused_mha_forward_varlen.cu:100-111).
+        const int rows = min(2 * BM, g.seqlen_q - m0);
+        uint16_t* outp = reinterpret_cast<uint16_t*>(p.out);
+        for (int idx = threadIdx.x; idx < rows * (D / 8); idx += blockDim.x) {
+            const int r = idx / (D / 8), c = idx % (D / 8);
+            uint16_t* dst = outp + o_b * p.o_stride_b + (int64_t)(g.q_off + m0 + r) * p.o_stride_s +
+                            head * p.o_stride_h + c * 8;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
+        for (int r = threadIdx.x; r < rows; r += blockDim.x)
+            p.lse[o_b * p.lse_stride_b + head * p.lse_stride_h + g.q_off + m0 + r] = kNegSentinel;
+        return;
+    }
+
+    // ------------------------------------------------------------------ shared-memory carve-up
+    const uint32_t sQ = sbase;
+    const uint32_t sKV = sbase + Cfg::kSmemQ;
+    const uint32_t bars = sbase + Cfg::kOffBars;
+    auto bar_q_full = [&](int s) { return bars + 8 * s; };
+    auto bar_kv_full = [&](int i) { return bars + 8 * (2 + i); };
+    auto bar_kv_empty = [&](int i) { return bars + 8 * (2 + KV + i); };
+    auto bar_s_full = [&](int s) { return bars + 8 * (2 + 2 * KV + s); };
+    auto bar_p_full = [&](int s) { return bars + 8 * (4 + 2 * KV + s); };
+    auto bar_stats = [&](int s) { return bars + 8 * (6 + 2 * KV + s); };
+    auto bar_final = [&](int s) { return bars + 8 * (8 + 2 * KV + s); };
+    auto bar_o_full = [&](int s) { return bars + 8 * (10 + 2 * KV + s); };
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffTmemPtr);
+    float* sScale = reinterpret_cast<float*>(sgen + Cfg::kOffScale);
+    float* sRowSum = reinterpret_cast<float*>(sgen + Cfg::kOffRowSum);
+    float* sRowMax = reinterpret_cast<float*>(sgen + Cfg::kOffRowMax);
+
+    if (warp == 13 && lane == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_q_full(s), 1);
+            mbar_init(bar_s_full(s), 1);
+            mbar_init(bar_p_full(s), 8);  // 4 softmax warps + 4 correction warps
+            mbar_init(bar_stats(s), 4);
+            mbar_init(bar_final(s), 4);
+            mbar_init(bar_o_full(s), 1);
+        }
+        for (int i = 0; i < KV; ++i) {
+            mbar_init(bar_kv_full(i), 1);
+            mbar_init(bar_kv_empty(i), 1);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&p.tm_q);
+        tma_prefetch_desc(&p.tm_k);
+        tma_prefetch_desc(&p.tm_v);
+    }
+    if (warp == 12) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int kv_head = head / p.heads_per_kv;
+
+    if (warp == 13) {
+        // ============================================================ TMA producer
+        reg_dec<48>();
+        auto load_tile = [&](const CUtensorMap* tm, uint32_t dst, uint32_t bar, int h, int row, int b) {
+            mbar_arrive_expect_tx(bar, Cfg::kTileBytes);
+#pragma unroll
+            for (int c = 0; c < D / 64; ++c)
+                tma_load_4d(dst + c * Cfg::kHalfBytes, tm, bar, c * 64, h, row, b);
+        };
+        auto kv_coords = [&](int n, int& row, int& b) {
+            const int r = n * BN;
+            if (p.block_table) {
+                const int page = r / p.page_size;
+                b = p.block_table[(int64_t)batch * p.block_table_stride + page];
+                row = r - page * p.page_size;
+            } else {
+                b = g.k_b;
+                row = g.k_off + r;
+            }
+        };
+        int ring = 0;
+        auto produce = [&](const CUtensorMap* tm, int n) {
+            const int slot = ring % KV;
+            const uint32_t parity = ((ring / KV) & 1) ^ 1;
+            mbar_wait(bar_kv_empty(slot), parity);
+            if (lane == 0) {
+                int row, b;
+                kv_coords(n, row, b);
+                load_tile(tm, sKV + slot * Cfg::kTileBytes, bar_kv_full(slot), kv_head, row, b);
+            }
+            ++ring;
+        };
+        if (lane == 0) load_tile(&p.tm_q, sQ, bar_q_full(0), head, g.q_off + m0, g.q_b);
+        produce(&p.tm_k, n_max - 1);
+        if (lane == 0)
+            load_tile(&p.tm_q, sQ + Cfg::kTileBytes, bar_q_full(1), head, g.q_off + m0 + BM, g.q_b);
+        produce(&p.tm_v, n_max - 1);
+        for (int it = 1; it < n_tiles; ++it) {
+            produce(&p.tm_k, n_max - 1 - it);
+            produce(&p.tm_v, n_max - 1 - it);
+        }
+    } else if (warp == 12) {
+        // ============================================================ MMA issuer
+        reg_dec<48>();
+        constexpr uint32_t idesc_qk = umma_idesc_f16(BF16, BM, BN, false, false);
+        constexpr uint32_t idesc_pv = umma_idesc_f16(BF16, BM, D, false, true);
+        const uint32_t tS[2] = {tmem_base + Cfg::kTmemS0, tmem_base + Cfg::kTmemS1};
+        const uint32_t tO[2] = {tmem_base + Cfg::kTmemO0, tmem_base + Cfg::kTmemO1};
+
+        // S_s = Q_s K^T : both operands K-major, 128B swizzle, 8-row groups 1024 B apart.
+        auto issue_qk = [&](int s, uint32_t k_smem) {
+            const uint32_t q_smem = sQ + s * Cfg::kTileBytes;
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+                const uint32_t koff = (kk / 4) * Cfg::kHalfBytes + (kk % 4) * 32;
+                umma_ss(tS[s], umma_desc_sw128(q_smem + koff, 16, 1024),
+                        umma_desc_sw128(k_smem + koff, 16, 1024), idesc_qk, kk > 0 ? 1u : 0u);
+            }
+        };
+        // O_s (+)= P_s V : A = P from TMEM (16-bit pairs, 8 columns per k-step of 16),
+        // B = V tile [kv rows][head_dim] = MN-major: 64-column blocks kHalfBytes apart (LBO),
+        // 8-row groups 1024 B apart (SBO); a k-step of 16 kv rows advances 2048 B.
+        auto issue_pv = [&](int s, uint32_t v_smem, bool accumulate) {
+            const uint32_t tP = tS[s] + Cfg::kTmemPOff;
+#pragma unroll
+            for (int kk = 0; kk < BN / 16; ++kk) {
+                umma_ts(tO[s], tP + kk * 8, umma_desc_sw128(v_smem + kk * 2048, Cfg::kHalfBytes, 1024),
+                        idesc_pv, (accumulate || kk > 0) ? 1u : 0u);
+            }
+        };
+
+        int ring = 0;
+        auto slot_addr = [&](int r) { return sKV + (r % KV) * Cfg::kTileBytes; };
+        auto wait_full = [&](int r) { mbar_wait(bar_kv_full(r % KV), (r / KV) & 1); };
+
+        // first K tile: S0, S1
+        wait_full(ring);
+        mbar_wait(bar_q_full(0), 0);
+        tc_fence_after();
+        if (lane == 0) {
+            issue_qk(0, slot_addr(ring));
+            umma_commit(bar_s_full(0));
+        }
+        __syncwarp();
+        mbar_wait(bar_q_full(1), 0);
+        tc_fence_after();
+        if (lane == 0) {
+            issue_qk(1, slot_addr(ring));
+            umma_commit(bar_s_full(1));
+            umma_commit(bar_kv_empty(ring % KV));
+        }
+        __syncwarp();
+        ++ring;
+
+        for (int it = 1; it < n_tiles; ++it) {
+            const int rv = ring, rk = ring + 1;  // V_{it-1}, K_it
+            wait_full(rv);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                mbar_wait(bar_p_full(s), (it - 1) & 1);
+                if (s == 0) wait_full(rk);
+                tc_fence_after();
+                if (lane == 0) {
+                    issue_pv(s, slot_addr(rv), it > 1);
+                    if (s == 1) umma_commit(bar_kv_empty(rv % KV));
+                    issue_qk(s, slot_addr(rk));
+                    umma_commit(bar_s_full(s));
+                    if (s == 1) umma_commit(bar_kv_empty(rk % KV));
+                }
+                __syncwarp();
+            }
+            ring += 2;
+        }
+        // last V tile
+        wait_full(ring);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            mbar_wait(bar_p_full(s), (n_tiles - 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                issue_pv(s, slot_addr(ring), n_tiles > 1);
+                umma_commit(bar_o_full(s));
+            }
+            __syncwarp();
+        }
+    } else if (warp < 8) {
+        // ============================================================ softmax (stage = warp / 4)
+        reg_inc<192>();
+        const int s = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tS = tmem_base + lane_off + (s == 0 ? Cfg::kTmemS0 : Cfg::kTmemS1);
+        const uint32_t tP = tS + Cfg::kTmemPOff;
+        const int i_glob = m0 + s * BM + row;  // row index inside the sequence
+
+        // visible key range of this row: [col_lo, col_hi)
+        int col_hi = g.seqlen_k;
+        if (p.window_right >= 0) col_hi = min(col_hi, i_glob + off + p.window_right + 1);
+        int col_lo = 0;
+        if (p.window_left >= 0) col_lo = max(0, i_glob + off - p.window_left);
+        const unsigned col_width = (unsigned)max(col_hi - col_lo, 0);
+
+        const float sl2 = FEAT ? 1.0f : p.scale_log2;
+        float slope = 0.f, inv_cap = 0.f;
+        if constexpr (FEAT) {
+            if (p.alibi) slope = p.alibi[batch * p.alibi_stride_b + head];
+            if (p.softcap > 0.f) inv_cap = 1.0f / p.softcap;
+        }
+
+        float m_ref = -INFINITY;  // running reference max (raw score units; log2 units if FEAT)
+        float row_sum = 0.f;
+
+        for (int it = 0; it < n_tiles; ++it) {
+            const int j0 = (n_max - 1 - it) * BN;
+            mbar_wait(bar_s_full(s), it & 1);
+            tc_fence_after();
+            float v[BN];
+            tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
+
+            if constexpr (FEAT) {
+                // reference order (include/mat_mul.h:111-117): scale, ALiBi, then softcap
+                const int rel0 = i_glob + off - j0;
+#pragma unroll
+                for (int c = 0; c < BN; ++c) {
+                    float u = v[c] * p.scale;
+                    u -= slope * fabsf((float)(rel0 - c));
+                    if (p.softcap > 0.f) u = p.softcap * tanh_approx(u * inv_cap);
+                    v[c] = u * kLog2e;
+                }
+            }
+            const bool need_mask = (j0 + BN > col_hi) || (j0 < col_lo);
+            if (__any_sync(0xffffffffu, need_mask)) {
+                const int base = j0 - col_lo;
+#pragma unroll
+                for (int c = 0; c < BN; ++c)
+                    v[c] = ((unsigned)(base + c) < col_width) ? v[c] : -INFINITY;
+            }
+
+            float mx0 = fmax3(v[0], v[1], v[2]), mx1 = fmax3(v[3], v[4], v[5]);
+#pragma unroll
+            for (int c = 6; c + 3 < BN; c += 4) {
+                mx0 = fmax3(mx0, v[c], v[c + 1]);
+                mx1 = fmax3(mx1, v[c + 2], v[c + 3]);
+            }
+            mx0 = fmax3(mx0, v[BN - 2], v[BN - 1]);
+            const float m_new = fmaxf(m_ref, fmaxf(mx0, mx1));
+            const float m_new_safe = (m_new == -INFINITY) ? 0.f : m_new;
+
+            float acc_scale = 1.0f;
+            if (it == 0) {
+                m_ref = m_new;
+            } else {
+                const float d = (m_ref - m_new_safe) * sl2;  // <= 0, -inf if nothing was visible yet
+                if (d < -kRescaleThreshold) {
+                    acc_scale = ex2_approx(d);
+                    m_ref = m_new;
+                }
+            }
+            sScale[s * BM + row] = acc_scale;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_stats(s));
+
+            const float m_used = (m_ref == -INFINITY) ? 0.f : m_ref;
+            const float neg_m = -m_used * sl2;
+            float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float p0 = ex2_approx(fmaf(v[ch * 32 + c], sl2, neg_m));
+                    const float p1 = ex2_approx(fmaf(v[ch * 32 + c + 1], sl2, neg_m));
+                    sum0 += p0;
+                    sum1 += p1;
+                    pk[c / 2] = pack2<BF16>(p0, p1);
+                }
+                tmem_st_x16(tP + ch * 16, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_p_full(s));
+            row_sum = row_sum * acc_scale + (sum0 + sum1);
+        }
+        sRowSum[s * BM + row] = row_sum;
+        sRowMax[s * BM + row] = ((m_ref == -INFINITY) ? 0.f : m_ref) * sl2;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_final(s));
+    } else if (warp < 12) {
+        // ============================================================ correction + epilogue
+        reg_dec<80>();
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tO[2] = {tmem_base + lane_off + Cfg::kTmemO0, tmem_base + lane_off + Cfg::kTmemO1};
+
+        for (int it = 0; it < n_tiles; ++it) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                mbar_wait(bar_stats(s), it & 1);
+                const float sc = sScale[s * BM + row];
+                if (it > 0 && __any_sync(0xffffffffu, sc != 1.0f)) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < D / 32; ++c) {
+                        float o[32];
+                        tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) o[e] *= sc;
+                        tmem_st_x32(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
+                    }
+                    tmem_wait_st();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_p_full(s));
+            }
+        }
+        // epilogue: out = O / l, lse = m + ln(l)   (reference kernel/fused_mha_forward.cu:215-223)
+        uint16_t* outp = reinterpret_cast<uint16_t*>(p.out);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            mbar_wait(bar_final(s), 0);
+            const float l = sRowSum[s * BM + row];
+            const float mx = sRowMax[s * BM + row];
+            mbar_wait(bar_o_full(s), 0);
+            tc_fence_after();
+            const int i_glob = m0 + s * BM + row;
+            const bool valid = i_glob < g.seqlen_q;
+            const float inv = l > 0.f ? 1.0f / l : 0.f;
+            uint16_t* dst = outp + o_b * p.o_stride_b + (int64_t)(g.q_off + i_glob) * p.o_stride_s +
+                            head * p.o_stride_h;
+#pragma unroll
+            for (int c = 0; c < D / 32; ++c) {
+                float o[32];
+                tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
+                if (valid) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 8) {
+                        uint4 w;
+                        w.x = pack2<BF16>(o[e] * inv, o[e + 1] * inv);
+                        w.y = pack2<BF16>(o[e + 2] * inv, o[e + 3] * inv);
+                        w.z = pack2<BF16>(o[e + 4] * inv, o[e + 5] * inv);
+                        w.w = pack2<BF16>(o[e + 6] * inv, o[e + 7] * inv);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + e) = w;
+                    }
+                }
+            }
+            if (valid) {
+                const float lse = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : kNegSentinel;
+                p.lse[o_b * p.lse_stride_b + head * p.lse_stride_h + g.q_off + i_glob] = lse;
+            }
+        }
+    } else {
+        reg_dec<48>();  // warps 14, 15: spare
+    }
+
+    // ------------------------------------------------------------------ teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace fa

@@ -1,0 +1,191 @@
+"""Python API: flash_attn_func / flash_attn_varlen_func / flash_attn_with_kvcache.
+
+Drop-in for reference flash_attn_v100/flash_attn_interface.py (signatures :115-127, :272-289,
+:323-343; aliases :393-401): same names, positional order, defaults and return conventions.
+What differs is below the API: the reference permutes (B,S,H,D)->(B,H,S,D) and calls
+`.contiguous()` three times on the way in and once on the way out (:36-53, :67); here the
+operator layer consumes strided views through TMA descriptors, so no tensor is copied.
+
+Forward only: the autograd.Function wrappers of the reference (:17-112, :157-269) exist there to
+route a backward pass that this build does not have; inputs that require grad
+are accepted but the result carries no grad_fn.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import traceback
+import warnings
+from typing import Optional, Tuple, Union
+
+import torch
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG_ROOT not in sys.path:
+    sys.path.insert(0, _PKG_ROOT)
+import flash_attn_v100_cuda  # noqa: E402  (the operator layer next to this package)
+
+
+def maybe_contiguous(x: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return x.contiguous() if x is not None and x.stride(-1) != 1 else x
+
+
+def _pad8(x: torch.Tensor, pad: int) -> torch.Tensor:
+    return torch.nn.functional.pad(x, [0, pad]) if pad else x
+
+
+# ======================================================================================
+# DENSE ATTENTION (B, M, H, D)
+# ======================================================================================
+def flash_attn_func(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    dropout_p: float = 0.0,
+    softmax_scale: float = None,
+    causal: bool = False,
+    window_size: Tuple[int, int] = (-1, -1),
+    softcap: float = 0.0,
+    alibi_slopes: Optional[torch.Tensor] = None,
+    deterministic: bool = False,
+    return_attn_probs: bool = False,
+):
+    """Dense Flash Attention (B, M, H, D)"""
+    if deterministic:
+        warnings.warn("Forward is always deterministic. Deterministic backward is not supported.", RuntimeWarning)
+        deterministic = False
+    try:
+        head_size_og = q.shape[-1]
+        pad = (8 - head_size_og % 8) % 8  # reference :44-49
+        q_, k_, v_ = (_pad8(maybe_contiguous(t), pad).permute(0, 2, 1, 3) for t in (q, k, v))
+        if softmax_scale is None:
+            softmax_scale = head_size_og ** -0.5  # from the unpadded dim, reference :55-56
+        window_left, window_right = window_size
+        out_, lse_, dmask_, _rng = flash_attn_v100_cuda.fwd(
+            q_, k_, v_, None, alibi_slopes,
+            dropout_p, softmax_scale, causal,
+            window_left, window_right, softcap,
+            return_attn_probs, None,
+        )
+        out = out_[..., :head_size_og].permute(0, 2, 1, 3)
+        if not out.is_contiguous():
+            out = out.contiguous()
+        return (out, lse_, dmask_) if return_attn_probs else out
+    except Exception as e:
+        print(f"[B200 FA2 DENSE FAILED] {type(e).__name__}: {e}")
+        traceback.print_exc()
+        raise
+
+
+# ======================================================================================
+# VARLEN ATTENTION (T, H, D)
+# ======================================================================================
+def flash_attn_varlen_func(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    cu_seqlens_q: torch.Tensor,
+    cu_seqlens_k: torch.Tensor,
+    max_seqlen_q: int,
+    max_seqlen_k: int,
+    dropout_p: float = 0.0,
+    softmax_scale: float = None,
+    causal: bool = False,
+    window_size: Tuple[int, int] = (-1, -1),
+    softcap: float = 0.0,
+    alibi_slopes: Optional[torch.Tensor] = None,
+    deterministic: bool = False,
+    return_attn_probs: bool = False,
+    block_table: Optional[torch.Tensor] = None,
+):
+    """Varlen Flash Attention (T, H, D)"""
+    if deterministic:
+        warnings.warn("Forward is always deterministic. Deterministic backward is not supported.", RuntimeWarning)
+        deterministic = False
+    try:
+        cu_seqlens_q = cu_seqlens_q.to(torch.int32).contiguous()
+        cu_seqlens_k = cu_seqlens_k.to(torch.int32).contiguous()
+        head_size_og = q.size(2)
+        pad = (8 - head_size_og % 8) % 8
+        q_, k_, v_ = (_pad8(maybe_contiguous(t), pad) for t in (q, k, v))
+        if softmax_scale is None:
+            softmax_scale = head_size_og ** -0.5
+        window_left, window_right = window_size
+        out, lse, dmask, _rng = flash_attn_v100_cuda.varlen_fwd(
+            q_, k_, v_, None, cu_seqlens_q, cu_seqlens_k,
+            None, None, block_table, alibi_slopes,
+            max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale,
+            False, causal, window_left, window_right, softcap,
+            return_attn_probs and dropout_p > 0.0, None, 0,
+        )
+        out = out[..., :head_size_og]
+        if not out.is_contiguous():
+            out = out.contiguous()
+        return (out, lse, dmask) if return_attn_probs else out
+    except Exception as e:
+        print(f"[B200 FA2 VARLEN FAILED] {type(e).__name__}: {e}")
+        traceback.print_exc()
+        raise
+
+
+# ======================================================================================
+# KV ATTENTION
+# ======================================================================================
+def flash_attn_with_kvcache(
+    q: torch.Tensor,
+    k_cache: torch.Tensor,
+    v_cache: torch.Tensor,
+    k: Optional[torch.Tensor] = None,
+    v: Optional[torch.Tensor] = None,
+    rotary_cos: Optional[torch.Tensor] = None,
+    rotary_sin: Optional[torch.Tensor] = None,
+    cache_seqlens: Optional[Union[int, torch.Tensor]] = None,
+    cache_batch_idx: Optional[torch.Tensor] = None,
+    cache_leftpad: Optional[torch.Tensor] = None,
+    block_table: Optional[torch.Tensor] = None,
+    softmax_scale: Optional[float] = None,
+    causal: bool = False,
+    window_size: Tuple[int, int] = (-1, -1),
+    softcap: float = 0.0,
+    rotary_interleaved: bool = True,
+    alibi_slopes: Optional[torch.Tensor] = None,
+    num_splits: int = 0,
+    return_softmax_lse: bool = False,
+) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+    """
+    FlashAttention with KV cache (B, M, H, D).
+    """
+    assert k_cache.stride(-1) == 1, "k_cache must have contiguous last dimension"
+    assert v_cache.stride(-1) == 1, "v_cache must have contiguous last dimension"
+
+    q, k, v = [maybe_contiguous(x) for x in (q, k, v)]
+    if softmax_scale is None:
+        softmax_scale = q.shape[-1] ** (-0.5)
+    if cache_seqlens is not None and isinstance(cache_seqlens, int):
+        cache_seqlens = torch.full((q.shape[0],), cache_seqlens, dtype=torch.int32, device=k_cache.device)
+
+    def _c(t):
+        return t.contiguous() if t is not None else None
+
+    out, softmax_lse = flash_attn_v100_cuda.fwd_kvcache(
+        q, k_cache, v_cache, k, v,
+        _c(cache_seqlens), rotary_cos, rotary_sin,
+        _c(cache_batch_idx), _c(cache_leftpad), _c(block_table),
+        alibi_slopes, None, softmax_scale, causal,
+        window_size[0], window_size[1], softcap,
+        rotary_interleaved, num_splits,
+    )
+    if return_softmax_lse:
+        return out, softmax_lse
+    return out
+
+
+flash_attn_gpu = flash_attn_func
+flash_attn_varlen_gpu = flash_attn_varlen_func
+flash_attn_with_kvcache_gpu = flash_attn_with_kvcache
+
+__all__ = [
+    "flash_attn_func", "flash_attn_gpu",
+    "flash_attn_varlen_func", "flash_attn_varlen_gpu",
+    "flash_attn_with_kvcache", "flash_attn_with_kvcache_gpu",
+]

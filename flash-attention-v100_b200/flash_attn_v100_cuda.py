@@ -1,0 +1,456 @@
+"""Operator layer of the B200 build: the module the Python API calls, with the reference's names.
+
+Mirrors the pybind11 module `flash_attn_v100_cuda` of ai-bond/flash-attention-v100
+(reference kernel/fused_mha_api.cpp:17-33; C++ signatures in reference include/mha.h): the same five
+callables, the same positional argument order and the same return lists
+
+    fwd(q, k, v, out, alibi_slopes, p_dropout, softmax_scale, is_causal, window_left, window_right,
+        softcap, return_softmax, gen)                      -> [out, lse, dmask, rng_state]
+    varlen_fwd(q, k, v, out, cu_seqlens_q, cu_seqlens_k, seqused_k, leftpad_k, block_table,
+        alibi_slopes, max_seqlen_q, max_seqlen_k, p_dropout, softmax_scale, zero_tensors, is_causal,
+        window_left, window_right, softcap, return_softmax, gen, num_splits)
+                                                           -> [out, lse, dmask, rng_state]
+    fwd_kvcache(q, kcache, vcache, k, v, seqlens_k, rotary_cos, rotary_sin, cache_batch_idx,
+        leftpad_k, block_table, alibi_slopes, out, softmax_scale, is_causal, window_left,
+        window_right, softcap, is_rotary_interleaved, num_splits) -> [out, lse]
+    bwd(...), varlen_bwd(...)                              -> NotImplementedError (forward-only build)
+
+Where the reference's wrappers (kernel/fused_mha_forward.cu:301-432, ..._varlen.cu:371-566,
+..._kvcache.cu:416-652) validate with TORCH_CHECK and allocate outputs with ATen, this module
+validates in Python (same messages where the reference has one), allocates with torch, and hands raw
+pointers + strides to the C ABI in libfa_b200.so (include/fa_b200.h) through ctypes. There is no
+CPU or PyTorch fallback: if the library is missing or the device is not sm_100 the call raises.
+
+Layout contract kept from the reference: `fwd` takes q,k,v as [B, H, S, D] (include/mha.h:12-15) --
+but by *strides*, so a permuted view of a [B, S, H, D] tensor is consumed in place (no copies).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.environ.get("FA_B200_LIB", os.path.join(_HERE, "lib", "libfa_b200.so"))
+
+FA_B200_DTYPE_FP16 = 0
+FA_B200_DTYPE_BF16 = 1
+KIND_DENSE, KIND_VARLEN, KIND_KVCACHE = 0, 1, 2
+
+_i32, _i64, _f32, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class FaB200Params(ctypes.Structure):
+    """ctypes mirror of fa_b200_params_t (include/fa_b200.h); tests/test_abi.py checks the match."""
+
+    _fields_ = [
+        ("struct_bytes", _i32), ("dtype", _i32), ("device", _i32), ("reserved0", _i32),
+        ("batch", _i32), ("seqlen_q", _i32), ("seqlen_k", _i32), ("num_heads", _i32),
+        ("num_heads_k", _i32), ("head_dim", _i32), ("total_q", _i32), ("total_k", _i32),
+        ("q", _ptr), ("k", _ptr), ("v", _ptr), ("out", _ptr), ("lse", _ptr),
+        ("q_stride_b", _i64), ("q_stride_s", _i64), ("q_stride_h", _i64),
+        ("k_stride_b", _i64), ("k_stride_s", _i64), ("k_stride_h", _i64),
+        ("v_stride_b", _i64), ("v_stride_s", _i64), ("v_stride_h", _i64),
+        ("o_stride_b", _i64), ("o_stride_s", _i64), ("o_stride_h", _i64),
+        ("batch_k", _i32), ("reserved1", _i32),
+        ("cu_seqlens_q", _ptr), ("cu_seqlens_k", _ptr), ("seqused_k", _ptr),
+        ("block_table", _ptr), ("block_table_stride", _i32), ("page_size", _i32),
+        ("num_pages", _i32), ("reserved2", _i32),
+        ("cache_seqlens", _ptr), ("cache_batch_idx", _ptr), ("cache_leftpad", _ptr),
+        ("k_new", _ptr), ("v_new", _ptr),
+        ("knew_stride_b", _i64), ("knew_stride_s", _i64), ("knew_stride_h", _i64),
+        ("vnew_stride_b", _i64), ("vnew_stride_s", _i64), ("vnew_stride_h", _i64),
+        ("seqlen_new", _i32), ("rotary_dim", _i32),
+        ("rotary_cos", _ptr), ("rotary_sin", _ptr),
+        ("rotary_seqlen", _i32), ("rotary_interleaved", _i32),
+        ("alibi_slopes", _ptr), ("alibi_stride_b", _i64),
+        ("softmax_scale", _f32), ("softcap", _f32),
+        ("is_causal", _i32), ("window_left", _i32), ("window_right", _i32), ("num_splits", _i32),
+        ("workspace", _ptr), ("workspace_bytes", _i64),
+    ]
+
+
+EXPORTED_SYMBOLS = (
+    "fa_b200_abi_version", "fa_b200_last_error", "fa_b200_workspace_bytes", "fa_b200_fwd",
+    "fa_b200_varlen_fwd", "fa_b200_kvcache_fwd", "fa_b200_launch_count",
+)
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libfa_b200.so (built by `__graft_entry__.build()` / csrc/build.sh). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"libfa_b200.so not found at {_LIB_PATH}: build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (there is no fallback path)")
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.fa_b200_abi_version.restype = ctypes.c_int
+    lib.fa_b200_last_error.restype = ctypes.c_char_p
+    lib.fa_b200_launch_count.restype = ctypes.c_int64
+    lib.fa_b200_workspace_bytes.restype = ctypes.c_int64
+    lib.fa_b200_workspace_bytes.argtypes = [ctypes.POINTER(FaB200Params), ctypes.c_int]
+    for name in ("fa_b200_fwd", "fa_b200_varlen_fwd", "fa_b200_kvcache_fwd"):
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.POINTER(FaB200Params), ctypes.c_void_p]
+    if lib.fa_b200_abi_version() != 1:
+        raise ImportError(f"libfa_b200.so ABI {lib.fa_b200_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def launch_count() -> int:
+    """CUDA kernels launched by libfa_b200.so so far in this process."""
+    return int(load_library().fa_b200_launch_count())
+
+
+def _check(cond: bool, msg: str) -> None:
+    # the reference raises c10::Error (a RuntimeError in Python) from TORCH_CHECK
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    _check(t.dtype in (torch.float16, torch.bfloat16), "q must be fp16 or bf16")
+    return FA_B200_DTYPE_FP16 if t.dtype == torch.float16 else FA_B200_DTYPE_BF16
+
+
+def _call(fn_name: str, params: FaB200Params, device: torch.device) -> None:
+    lib = load_library()
+    params.struct_bytes = ctypes.sizeof(FaB200Params)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = getattr(lib, fn_name)(ctypes.byref(params), ctypes.c_void_p(stream))
+    if rc != 0:
+        msg = lib.fa_b200_last_error().decode("utf-8", "replace")
+        if rc == -2:
+            raise NotImplementedError(msg)
+        raise RuntimeError(f"{fn_name} failed ({rc}): {msg}")
+
+
+def _padded_dim(d: int) -> int:
+    _check(d <= 256, "head dimension must be <= 256")
+    _check(d % 8 == 0, "head dimension must be multiple of 8")
+    if d <= 64:
+        return 64
+    if d <= 128:
+        return 128
+    raise NotImplementedError(f"head_dim {d} > 128 is not built yet (SURVEY 8f rank 3)")
+
+
+def _pad_last(x: Optional[torch.Tensor], d_to: int) -> Optional[torch.Tensor]:
+    if x is None or x.shape[-1] == d_to:
+        return x
+    return torch.nn.functional.pad(x, [0, d_to - x.shape[-1]])
+
+
+def _aligned(x: torch.Tensor) -> torch.Tensor:
+    """TMA needs a 16-byte aligned base and strides that are multiples of 8 elements."""
+    ok = x.stride(-1) == 1 and x.data_ptr() % 16 == 0 and all(s % 8 == 0 for s in x.stride()[:-1])
+    return x if ok else x.contiguous()
+
+
+def _alibi(p: FaB200Params, alibi_slopes: Optional[torch.Tensor], batch: int, heads: int, keep: list) -> None:
+    if alibi_slopes is None:
+        return
+    s = alibi_slopes
+    _check(s.dtype == torch.float32 and s.is_cuda, "alibi_slopes must be fp32 on CUDA")
+    _check(s.stride(-1) == 1, "alibi_slopes last dim must be contiguous")
+    valid = (s.dim() == 1 and s.shape[0] == heads) or (s.dim() == 2 and tuple(s.shape) == (batch, heads))
+    _check(valid, "alibi_slopes must be [H_Q] or [B, H_Q]")
+    p.alibi_slopes = s.data_ptr()
+    p.alibi_stride_b = s.stride(0) if s.dim() == 2 else 0
+    keep.append(s)
+
+
+def _no_dropout(p_dropout: float, return_softmax: bool, softcap: float) -> None:
+    _check(0.0 <= p_dropout < 1.0, "p_dropout must be in [0, 1)")
+    if softcap > 0.0:
+        _check(p_dropout == 0.0, "Softcapping does not support dropout")
+    _check((not return_softmax) or p_dropout > 0.0, "return_softmax requires p_dropout > 0")
+    if p_dropout > 0.0:
+        raise NotImplementedError("dropout in the forward is not built yet (SURVEY 8f rank 1)")
+
+
+# ======================================================================================
+# dense:  replaces flash_attention_forward (reference kernel/fused_mha_forward.cu:301-432)
+# ======================================================================================
+def fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, window_left, window_right,
+        softcap, return_softmax, gen_) -> List[torch.Tensor]:
+    _check(q.is_cuda and k.is_cuda and v.is_cuda, "Tensors q, k, v must be on CUDA")
+    dt = _dtype_code(q)
+    _check(k.dtype == q.dtype and v.dtype == q.dtype, "k/v must have the same dtype as q")
+    _check(q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1, "Last dim of q, k, v must be contiguous")
+    B, H, M, D = q.shape
+    Hk, N = k.shape[1], k.shape[2]
+    _check(B > 0, "batch size must be positive")
+    _check(H % Hk == 0, "H_Q must be divisible by H_K for GQA/MQA")
+    _no_dropout(p_dropout, return_softmax, softcap)
+    Dp = _padded_dim(D)
+
+    lse = torch.empty((B, H, M), dtype=torch.float32, device=q.device)
+    dmask = torch.empty((0,), dtype=q.dtype, device=q.device)
+    rng_state = torch.zeros((2,), dtype=torch.int64, device=q.device)
+    if out_ is not None:
+        _check(out_.dtype == q.dtype, "out must have the same dtype as q")
+        _check(out_.is_cuda, "out must be on CUDA")
+        _check(out_.stride(-1) == 1, "out must have contiguous last dimension")
+        _check(out_.shape == q.shape, "out shape must match q shape")
+    if N == 0 or M == 0:  # reference :409-413
+        out = out_ if out_ is not None else torch.empty_like(q)
+        out.zero_()
+        lse.fill_(float("-inf"))
+        return [out, lse, dmask, rng_state]
+
+    qp, kp, vp = (_aligned(_pad_last(t, Dp)) for t in (q, k, v))
+    direct = out_ is not None and Dp == D and _aligned(out_) is out_
+    out = out_ if direct else torch.empty_like(qp)
+    if not (out.data_ptr() % 16 == 0 and all(s % 8 == 0 for s in out.stride()[:-1])):
+        out = torch.empty(qp.shape, dtype=q.dtype, device=q.device)
+
+    p = FaB200Params()
+    keep = [qp, kp, vp, out, lse]
+    p.dtype, p.device = dt, q.device.index if q.device.index is not None else torch.cuda.current_device()
+    p.batch, p.seqlen_q, p.seqlen_k, p.num_heads, p.num_heads_k, p.head_dim = B, M, N, H, Hk, Dp
+    p.q, p.k, p.v, p.out, p.lse = qp.data_ptr(), kp.data_ptr(), vp.data_ptr(), out.data_ptr(), lse.data_ptr()
+    # tensors are [B, H, S, D]: batch stride 0, head stride 1, row stride 2
+    p.q_stride_b, p.q_stride_h, p.q_stride_s = qp.stride(0), qp.stride(1), qp.stride(2)
+    p.k_stride_b, p.k_stride_h, p.k_stride_s = kp.stride(0), kp.stride(1), kp.stride(2)
+    p.v_stride_b, p.v_stride_h, p.v_stride_s = vp.stride(0), vp.stride(1), vp.stride(2)
+    p.o_stride_b, p.o_stride_h, p.o_stride_s = out.stride(0), out.stride(1), out.stride(2)
+    _alibi(p, alibi_slopes_, B, H, keep)
+    p.softmax_scale, p.softcap = float(softmax_scale), float(softcap)
+    p.is_causal, p.window_left, p.window_right = int(bool(is_causal)), int(window_left), int(window_right)
+    _call("fa_b200_fwd", p, q.device)
+
+    if not direct:
+        res = out[..., :D]
+        if out_ is not None:
+            out_.copy_(res)
+            res = out_
+        out = res
+    return [out, lse, dmask, rng_state]
+
+
+# ======================================================================================
+# varlen:  replaces flash_attention_varlen_forward (reference kernel/fused_mha_forward_varlen.cu:371-566)
+# ======================================================================================
+def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k_, leftpad_k_, block_table_, alibi_slopes_,
+               max_seqlen_q, max_seqlen_k, p_dropout, softmax_scale, zero_tensors, is_causal, window_left,
+               window_right, softcap, return_softmax, gen_, num_splits=0) -> List[torch.Tensor]:
+    _check(q.is_cuda and k.is_cuda and v.is_cuda, "Tensors q, k, v must be on CUDA")
+    dt = _dtype_code(q)
+    _check(k.dtype == q.dtype and v.dtype == q.dtype, "k/v must have the same dtype as q")
+    _check(q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1, "Last dim of q, k, v must be contiguous")
+    _check(num_splits <= 1, "num_splits > 1 not supported")
+    _check(leftpad_k_ is None, "leftpad_k is not supported by the varlen forward")  # reference ignores it
+    for name, t in (("cu_seqlens_q", cu_seqlens_q), ("cu_seqlens_k", cu_seqlens_k)):
+        _check(t.dtype == torch.int32 and t.dim() == 1 and t.is_cuda and t.is_contiguous(),
+               f"{name} must be a contiguous 1-D int32 CUDA tensor")
+    paged = block_table_ is not None
+    T, H, D = q.shape
+    B = cu_seqlens_q.numel() - 1
+    _check(B > 0, "batch size must be positive")
+    _check(cu_seqlens_k.numel() == B + 1, "cu_seqlens_k must have batch + 1 entries")
+    if paged:
+        _check(block_table_.dtype == torch.int32 and block_table_.is_cuda, "block_table must be int32 on CUDA")
+        _check(block_table_.stride(-1) == 1, "block_table must have contiguous last dimension")
+        _check(k.dim() == 4 and v.dim() == 4, "paged k/v must be [num_blocks, page_block_size, H_K, D]")
+        num_pages, page, Hk = k.shape[0], k.shape[1], k.shape[2]
+        _check(page % 256 == 0, "page_block_size must be a multiple of 256")
+        _check(block_table_.shape[0] == B, "block_table must have one row per sequence")
+    else:
+        Hk = k.shape[1]
+    _check(H % Hk == 0, "H_Q must be divisible by H_K for GQA/MQA")
+    if seqused_k_ is not None:
+        _check(seqused_k_.dtype == torch.int32 and seqused_k_.is_cuda and seqused_k_.is_contiguous()
+               and seqused_k_.numel() == B, "seqused_k must be a contiguous int32 CUDA tensor of size batch")
+    _no_dropout(p_dropout, return_softmax, softcap)
+    Dp = _padded_dim(D)
+
+    lse = torch.empty((H, T), dtype=torch.float32, device=q.device)
+    dmask = torch.empty((0,), dtype=q.dtype, device=q.device)
+    rng_state = torch.zeros((2,), dtype=torch.int64, device=q.device)
+    if out_ is not None:
+        _check(out_.dtype == q.dtype and out_.is_cuda and out_.stride(-1) == 1 and out_.shape == q.shape,
+               "out must match q in dtype, device and shape with a contiguous last dimension")
+    if T == 0 or max_seqlen_q == 0:
+        out = out_ if out_ is not None else torch.empty_like(q)
+        return [out, lse, dmask, rng_state]
+
+    qp, kp, vp = (_aligned(_pad_last(t, Dp)) for t in (q, k, v))
+    direct = out_ is not None and Dp == D and _aligned(out_) is out_
+    out = out_ if direct else torch.empty((T, H, Dp), dtype=q.dtype, device=q.device)
+    if zero_tensors or max_seqlen_k == 0:
+        out.zero_()
+        lse.fill_(float("-inf") if not zero_tensors else 0.0)
+    if max_seqlen_k == 0:
+        return [out[..., :D] if not direct else out, lse, dmask, rng_state]
+
+    p = FaB200Params()
+    keep = [qp, kp, vp, out, lse, cu_seqlens_q, cu_seqlens_k]
+    p.dtype, p.device = dt, q.device.index if q.device.index is not None else torch.cuda.current_device()
+    p.batch, p.seqlen_q, p.seqlen_k, p.num_heads, p.num_heads_k, p.head_dim = B, int(max_seqlen_q), int(max_seqlen_k), H, Hk, Dp
+    p.total_q = T
+    p.q, p.k, p.v, p.out, p.lse = qp.data_ptr(), kp.data_ptr(), vp.data_ptr(), out.data_ptr(), lse.data_ptr()
+    p.q_stride_s, p.q_stride_h = qp.stride(0), qp.stride(1)
+    p.o_stride_s, p.o_stride_h = out.stride(0), out.stride(1)
+    if paged:
+        p.k_stride_b, p.k_stride_s, p.k_stride_h = kp.stride(0), kp.stride(1), kp.stride(2)
+        p.v_stride_b, p.v_stride_s, p.v_stride_h = vp.stride(0), vp.stride(1), vp.stride(2)
+        p.block_table, p.block_table_stride = block_table_.data_ptr(), block_table_.stride(0)
+        p.page_size, p.num_pages = page, num_pages
+        keep.append(block_table_)
+    else:
+        p.total_k = kp.shape[0]
+        p.k_stride_s, p.k_stride_h = kp.stride(0), kp.stride(1)
+        p.v_stride_s, p.v_stride_h = vp.stride(0), vp.stride(1)
+    p.cu_seqlens_q, p.cu_seqlens_k = cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr()
+    if seqused_k_ is not None:
+        p.seqused_k = seqused_k_.data_ptr()
+        keep.append(seqused_k_)
+    _alibi(p, alibi_slopes_, B, H, keep)
+    p.softmax_scale, p.softcap = float(softmax_scale), float(softcap)
+    p.is_causal, p.window_left, p.window_right = int(bool(is_causal)), int(window_left), int(window_right)
+    p.num_splits = int(num_splits)
+    _call("fa_b200_varlen_fwd", p, q.device)
+
+    if not direct:
+        res = out[..., :D]
+        if out_ is not None:
+            out_.copy_(res)
+            res = out_
+        out = res
+    return [out, lse, dmask, rng_state]
+
+
+# ======================================================================================
+# kv-cache:  replaces flash_attention_kvcache (reference kernel/fused_mha_forward_kvcache.cu:416-652)
+# ======================================================================================
+def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_, cache_batch_idx_, leftpad_k_,
+                block_table_, alibi_slopes_, out_, softmax_scale, is_causal, window_left, window_right, softcap,
+                is_rotary_interleaved, num_splits) -> List[torch.Tensor]:
+    _check(q.is_cuda and kcache.is_cuda and vcache.is_cuda, "q, kcache, vcache must be on CUDA")
+    dt = _dtype_code(q)
+    _check(kcache.dtype == q.dtype and vcache.dtype == q.dtype, "kcache/vcache must have the same dtype as q")
+    _check(q.stride(-1) == 1 and kcache.stride(-1) == 1 and vcache.stride(-1) == 1, "Last dim must be contiguous")
+    B, Sq, H, D = q.shape
+    paged = block_table_ is not None
+    _check(D in (64, 128), "the kv-cache path needs head_dim 64 or 128 (the cache cannot be padded in place)")
+    if paged:
+        _check(block_table_.dtype == torch.int32 and block_table_.is_cuda, "block_table must be int32 on CUDA")
+        _check(block_table_.stride(-1) == 1, "block_table must have contiguous last dimension")
+        _check(cache_batch_idx_ is None, "Paged KV cache does not support cache_batch_idx")
+        _check(leftpad_k_ is None, "Paged KV cache does not support cache_leftpad")
+        num_pages, page, Hk = kcache.shape[0], kcache.shape[1], kcache.shape[2]
+        _check(page % 256 == 0, "page_block_size must be a multiple of 256")
+        _check(block_table_.shape[0] == B, "block_table must have one row per sequence")
+        capacity = block_table_.shape[1] * page
+        batch_c = 0
+    else:
+        batch_c, capacity, Hk = kcache.shape[0], kcache.shape[1], kcache.shape[2]
+        if cache_batch_idx_ is None:
+            _check(batch_c == B, "batch size of the cache must match q without cache_batch_idx")
+    _check(H % Hk == 0, "H_Q must be divisible by H_K for GQA/MQA")
+    _check(vcache.shape == kcache.shape, "kcache and vcache must have the same shape")
+    _check(num_splits <= 1, "num_splits > 1 not supported")  # reference :462 (0/1 = library decides)
+    if softcap > 0.0:
+        _check(window_left < 0 and window_right < 0, "softcap does not support window")
+        _check(alibi_slopes_ is None, "softcap does not support alibi")
+
+    def _i32vec(t, name):
+        _check(t.dtype == torch.int32 and t.is_cuda and t.is_contiguous() and t.numel() == B,
+               f"{name} must be a contiguous int32 CUDA tensor of size batch")
+        return t
+
+    p = FaB200Params()
+    keep = [q, kcache, vcache]
+    seqlen_new = 0
+    if k_ is not None or v_ is not None:
+        _check(k_ is not None and v_ is not None, "k and v must be provided together")
+        _check(seqlens_k_ is not None, "seqlens_k is required when appending k/v")
+        _check(k_.dtype == q.dtype and v_.dtype == q.dtype, "k/v must have the same dtype as q")
+        _check(k_.shape == v_.shape and k_.shape[0] == B and k_.shape[2] == Hk and k_.shape[3] == D,
+               "k/v must be [B, S_new, H_K, D]")
+        k_, v_ = _aligned(k_), _aligned(v_)
+        seqlen_new = k_.shape[1]
+        p.k_new, p.v_new, p.seqlen_new = k_.data_ptr(), v_.data_ptr(), seqlen_new
+        p.knew_stride_b, p.knew_stride_s, p.knew_stride_h = k_.stride(0), k_.stride(1), k_.stride(2)
+        p.vnew_stride_b, p.vnew_stride_s, p.vnew_stride_h = v_.stride(0), v_.stride(1), v_.stride(2)
+        keep += [k_, v_]
+    if seqlens_k_ is not None:
+        p.cache_seqlens = _i32vec(seqlens_k_, "seqlens_k").data_ptr()
+        keep.append(seqlens_k_)
+    if cache_batch_idx_ is not None:
+        p.cache_batch_idx = _i32vec(cache_batch_idx_, "cache_batch_idx").data_ptr()
+        keep.append(cache_batch_idx_)
+    if leftpad_k_ is not None:
+        p.cache_leftpad = _i32vec(leftpad_k_, "leftpad_k").data_ptr()
+        keep.append(leftpad_k_)
+    if rotary_cos_ is not None or rotary_sin_ is not None:
+        _check(rotary_cos_ is not None and rotary_sin_ is not None, "rotary_cos and rotary_sin must be given together")
+        _check(k_ is not None, "rotary requires k/v to append")
+        _check(rotary_cos_.dtype == q.dtype and rotary_sin_.dtype == q.dtype, "rotary cos/sin must have the dtype of q")
+        _check(rotary_cos_.is_contiguous() and rotary_sin_.is_contiguous(), "rotary cos/sin must be contiguous")
+        _check(rotary_cos_.shape == rotary_sin_.shape and rotary_cos_.dim() == 2, "rotary cos/sin must be [seqlen_ro, rotary_dim/2]")
+        rotary_dim = 2 * rotary_cos_.shape[1]
+        _check(rotary_dim <= D, "rotary_dim must be <= head_dim")
+        _check(rotary_dim % 16 == 0, "rotary_dim must be multiple of 16")
+        _check(rotary_cos_.shape[0] >= capacity, "rotary seqlen must cover the cache length")
+        p.rotary_cos, p.rotary_sin = rotary_cos_.data_ptr(), rotary_sin_.data_ptr()
+        p.rotary_dim, p.rotary_seqlen = rotary_dim, rotary_cos_.shape[0]
+        p.rotary_interleaved = int(bool(is_rotary_interleaved))
+        keep += [rotary_cos_, rotary_sin_]
+
+    qa = _aligned(q)
+    if out_ is not None:
+        _check(out_.dtype == q.dtype and out_.is_cuda and out_.stride(-1) == 1 and out_.shape == q.shape,
+               "out must match q in dtype, device and shape with a contiguous last dimension")
+    direct = out_ is not None and _aligned(out_) is out_
+    out = out_ if direct else torch.empty((B, Sq, H, D), dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+    keep += [qa, out, lse]
+
+    p.dtype, p.device = dt, q.device.index if q.device.index is not None else torch.cuda.current_device()
+    p.batch, p.seqlen_q, p.seqlen_k, p.num_heads, p.num_heads_k, p.head_dim = B, Sq, capacity, H, Hk, D
+    p.batch_k = batch_c
+    p.q, p.k, p.v, p.out, p.lse = qa.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), out.data_ptr(), lse.data_ptr()
+    p.q_stride_b, p.q_stride_s, p.q_stride_h = qa.stride(0), qa.stride(1), qa.stride(2)
+    p.o_stride_b, p.o_stride_s, p.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
+    p.k_stride_b, p.k_stride_s, p.k_stride_h = kcache.stride(0), kcache.stride(1), kcache.stride(2)
+    p.v_stride_b, p.v_stride_s, p.v_stride_h = vcache.stride(0), vcache.stride(1), vcache.stride(2)
+    if paged:
+        p.block_table, p.block_table_stride = block_table_.data_ptr(), block_table_.stride(0)
+        p.page_size, p.num_pages = page, num_pages
+        keep.append(block_table_)
+    _alibi(p, alibi_slopes_, B, H, keep)
+    p.softmax_scale, p.softcap = float(softmax_scale), float(softcap)
+    p.is_causal, p.window_left, p.window_right = int(bool(is_causal)), int(window_left), int(window_right)
+    p.num_splits = int(num_splits)
+
+    lib = load_library()
+    p.struct_bytes = ctypes.sizeof(FaB200Params)
+    ws_bytes = int(lib.fa_b200_workspace_bytes(ctypes.byref(p), KIND_KVCACHE))
+    if ws_bytes > 0:
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
+        keep.append(ws)
+    _call("fa_b200_kvcache_fwd", p, q.device)
+    if not direct and out_ is not None:
+        out_.copy_(out)
+        out = out_
+    return [out, lse]
+
+
+def bwd(*args, **kwargs):
+    raise NotImplementedError("backward is outside this build's scope (forward hot path only; SURVEY 8f rank 2)")
+
+
+def varlen_bwd(*args, **kwargs):
+    raise NotImplementedError("backward is outside this build's scope (forward hot path only; SURVEY 8f rank 2)")

@@ -1,0 +1,96 @@
+#!/usr/bin/env python3
+"""Quick on-GPU diagnostic: a handful of shapes against the CPU oracle plus a coarse timing.
+Writes gpurun_out/quick.json. Not a test and not the bench -- a bring-up tool."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "flash-attention-v100_b200"))
+from flash_attn_v100 import flash_attn_func  # noqa: E402
+from oracle.attention_oracle import (fa_tolerance_ok, flash_attn_func_ref, naive_lowp_attention,  # noqa: E402
+                                     normalize_mask_args)
+
+results = []
+
+
+def run_case(name, B, Sq, Sk, H, Hk, D, dtype, causal, window=(-1, -1), softcap=0.0, alibi=False):
+    torch.manual_seed(421)
+    dev = "cuda"
+    q = torch.randn(B, Sq, H, D, device=dev, dtype=dtype)
+    k = torch.randn(B, Sk, Hk, D, device=dev, dtype=dtype)
+    v = torch.randn(B, Sk, Hk, D, device=dev, dtype=dtype)
+    slopes = (torch.rand(H, device=dev, dtype=torch.float32) * 0.3) if alibi else None
+    rec = {"name": name}
+    try:
+        out, lse, _ = None, None, None
+        res = flash_attn_func(q, k, v, causal=causal, window_size=window, softcap=softcap, alibi_slopes=slopes)
+        torch.cuda.synchronize()
+        out = res
+        ref, lse_ref = flash_attn_func_ref(q, k, v, causal=causal, window_size=window, softcap=softcap,
+                                           alibi_slopes=slopes)
+        wl, wr = normalize_mask_args(Sq, Sk, causal, window, alibi)
+        naive = naive_lowp_attention(q, k, v, D ** -0.5, wl, wr) if (softcap == 0 and not alibi) else None
+        err = (out.double().cpu() - ref).abs().max().item()
+        rec["max_err"] = err
+        rec["finite"] = bool(torch.isfinite(out.float()).all().item())
+        if naive is not None:
+            ok, e, en = fa_tolerance_ok(out, ref, naive)
+            rec.update(ok=ok, err_naive=en)
+        else:
+            rec["ok"] = err < 2e-2
+        # per-row-block error map to localise layout bugs
+        e_rows = (out.double().cpu() - ref).abs().amax(dim=(0, 2, 3))
+        rec["err_by_rowblock"] = [round(x, 4) for x in e_rows.view(-1, min(64, Sq)).amax(dim=1).tolist()[:16]]
+    except Exception as ex:  # noqa: BLE001
+        rec["error"] = f"{type(ex).__name__}: {ex}"
+    print(json.dumps(rec), flush=True)
+    results.append(rec)
+
+
+def bench_case(name, B, S, H, Hk, D, dtype, causal, iters=10):
+    dev = "cuda"
+    torch.manual_seed(421)
+    q = torch.randn(B, S, H, D, device=dev, dtype=dtype)
+    k = torch.randn(B, S, Hk, D, device=dev, dtype=dtype)
+    v = torch.randn(B, S, Hk, D, device=dev, dtype=dtype)
+    for _ in range(3):
+        flash_attn_func(q, k, v, causal=causal)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        flash_attn_func(q, k, v, causal=causal)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 4 * B * H * S * S * D * (0.5 if causal else 1.0)
+    rec = {"name": name, "ms": ms, "tflops": flops / ms / 1e9}
+    print(json.dumps(rec), flush=True)
+    results.append(rec)
+
+
+if __name__ == "__main__":
+    f16, bf16 = torch.float16, torch.bfloat16
+    t0 = time.time()
+    run_case("d128_bf16_full_256", 1, 256, 256, 1, 1, 128, bf16, False)
+    run_case("d128_bf16_full_128x384", 1, 128, 384, 2, 2, 128, bf16, False)
+    run_case("d128_bf16_causal_512", 2, 512, 512, 4, 4, 128, bf16, True)
+    run_case("d64_f16_full_512_C1", 2, 512, 512, 8, 8, 64, f16, False)
+    run_case("d64_bf16_causal_1024", 1, 1024, 1024, 4, 2, 64, bf16, True)
+    run_case("d128_f16_causal_ragged", 2, 333, 777, 4, 2, 128, f16, True)
+    run_case("d128_bf16_window", 1, 1024, 1024, 2, 2, 128, bf16, True, window=(256, 0))
+    run_case("d128_bf16_softcap", 1, 512, 512, 2, 2, 128, bf16, False, softcap=30.0)
+    run_case("d128_bf16_alibi", 1, 512, 512, 2, 2, 128, bf16, True, alibi=True)
+    run_case("d128_bf16_causal_2048_gqa", 1, 2048, 2048, 8, 2, 128, bf16, True)
+    if all(r.get("ok") for r in results):
+        bench_case("C2_bf16_B8_H32_S4096_D128_causal", 8, 4096, 32, 32, 128, bf16, True)
+        bench_case("bf16_B8_H32_S4096_D128_full", 8, 4096, 32, 32, 128, bf16, False)
+        bench_case("C1_f16_B2_H8_S512_D64_full", 2, 512, 8, 8, 64, f16, False)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(results, open(os.path.join(ROOT, "gpurun_out", "quick.json"), "w"), indent=1)
+    print("elapsed", time.time() - t0)
