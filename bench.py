@@ -43,8 +43,8 @@ WORKLOADS = {
                desc="bf16 B=8 H=32 Hk=32 S=4096 D=128 causal per GPU (BASELINE config 2, Llama-3-8B shape)"),
     "c2gqa": dict(batch=8, heads=32, heads_k=8, seqlen=4096, head_dim=128, causal=True, window=(-1, -1),
                   desc="bf16 B=8 H=32 Hk=8 S=4096 D=128 causal per GPU (config 2 with Llama-3-8B GQA)"),
-    "c5": dict(batch=8, heads=32, heads_k=32, seqlen=8192, head_dim=128, causal=True, window=(4096, 0),
-               desc="bf16 B=8 H=32 S=8192 D=128 causal + window 4096 per GPU (BASELINE config 5 shard at 8 GPUs)"),
+    "c5": dict(batch=64, heads=32, heads_k=32, seqlen=8192, head_dim=128, causal=True, window=(4096, 0), strong=True,
+               desc="bf16 B=64 (global, sharded over the ranks) H=32 S=8192 D=128 causal + window 4096 (BASELINE config 5)"),
 }
 
 
@@ -69,47 +69,61 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons through NVML while the timed region runs
+    (every ~2 ms; `nvidia-smi` is far too slow for a region of tens of milliseconds)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.sm, self.power, self.reasons = [], [], set()
+        self.sm_max = None
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self._nvml = None
 
     def _run(self):
+        n = self._nvml
+        names = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else n.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", None) or n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", None) or n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", None) or n.nvmlClocksThrottleReasonSwPowerCap}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                self.power.append(n.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+                mask = get_reasons(self._h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002)
 
     def __enter__(self):
-        self._t.start()
+        if self._nvml is not None:
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._nvml is not None:
+            self._t.join(timeout=2)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.sm_max,
+                "power_w_max": max(self.power) if self.power else None, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------------------------------- reference arm
@@ -193,6 +207,12 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
+    import sharding
+
+    strong = bool(w.get("strong"))
+    if strong:  # fixed global batch, each rank takes its contiguous slice (config 5)
+        b0, b1 = sharding.shard_range(w["batch"], world, rank)
+        w = dict(w, batch=b1 - b0)
     B, H, Hk, S, D = w["batch"], w["heads"], w["heads_k"], w["seqlen"], w["head_dim"]
     causal, window = w["causal"], w["window"]
     torch.manual_seed(421 + rank)  # each rank generates its own shard locally
@@ -221,11 +241,9 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
     launches = op.launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
-    value = world * flops_rank * args.steps / (max_ms * 1e-3) / 1e12
+    max_ms = sharding.max_over_ranks(total_ms, dist, dev)
+    flops_all = sum(sharding.gather_checksums(flops_rank, dist, dev))  # whole-job work per step
+    value = flops_all * args.steps / (max_ms * 1e-3) / 1e12
 
     # ---- e2e: host pinned buffers -> H2D -> kernel -> D2H, pipelined over batch elements on two streams
     hq, hk, hv = (torch.randn(x.shape, dtype=torch.bfloat16).pin_memory() for x in (q, k, v))
@@ -255,10 +273,7 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * flops_rank * e2e_steps / float(t.item()) / 1e12
+    e2e_value = flops_all * e2e_steps / sharding.max_over_ranks(e2e_s, dist, dev) / 1e12
     h2d = sum(x.numel() * 2 for x in (hq, hk, hv))
     d2h = hout.numel() * 2
 
@@ -278,9 +293,9 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
         traffic = json.load(open(tpath)).get(args.workload)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": w["desc"], "global_batch": B * world, "seq_len": S, "heads": H, "heads_k": Hk,
+        "config": {"workload": w["desc"], "global_batch": WORKLOADS[args.workload]["batch"] * (1 if strong else world), "seq_len": S, "heads": H, "heads_k": Hk,
                    "head_dim": D, "parallelism": f"batch-sharded x{world}, no data-path collective",
                    "l2": "inputs+output 1 GiB per step exceed the 126 MB L2 (no flush needed)",
                    "flops_per_step_per_gpu": flops_rank},

@@ -6,12 +6,15 @@ out="${here}/../lib"
 mkdir -p "${out}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 python3 "${here}/gen_tmem_ldst.py" "${here}/tmem_ldst_gen.cuh"
-"${NVCC}" -std=c++17 -O3 -lineinfo \
+python3 "${here}/gen_umma_issue.py" "${here}/umma_issue_gen.cuh"
+# FA_VARIANT_FLAGS / FA_LIB_NAME: build an A/B variant (e.g. -DFA_EMU_COUNT=0) next to the default library
+LIB_NAME="${FA_LIB_NAME:-libfa_b200.so}"
+"${NVCC}" -std=c++17 -O3 -lineinfo ${FA_VARIANT_FLAGS:-} \
   -gencode arch=compute_100a,code=sm_100a \
   -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
   --expt-relaxed-constexpr \
   -Xptxas -v \
   -shared -cudart static \
-  -o "${out}/libfa_b200.so" "${here}/fa_b200_api.cu" 2> "${out}/ptxas.log" || { cat "${out}/ptxas.log"; exit 1; }
+  -o "${out}/${LIB_NAME}" "${here}/fa_b200_api.cu" 2> "${out}/ptxas.log" || { cat "${out}/ptxas.log"; exit 1; }
 grep -E "error|warning" "${out}/ptxas.log" | grep -v "Wno" | head -20 || true
-echo "built ${out}/libfa_b200.so"
+echo "built ${out}/${LIB_NAME}"

@@ -28,6 +28,7 @@
 #include <cstdint>
 
 #include "ptx_sm100.cuh"
+#include "umma_issue_gen.cuh"
 
 namespace fa {
 
@@ -68,6 +69,17 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kNegSentinel = -1e30f;  // reference NEG_INF (include/kernel.h:20) as the "no keys" LSE
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; O is rescaled only when the max moves more
 
+// Tuning knobs (compile-time; csrc/build.sh can override them with -D for A/B runs on the GPU).
+#ifndef FA_EMU_PERIOD
+#define FA_EMU_PERIOD 4  // of every FA_EMU_PERIOD pairs of exponentials ...
+#endif
+#ifndef FA_EMU_COUNT
+#define FA_EMU_COUNT 1   // ... this many are evaluated on the FMA pipes (ex2_emu2) instead of the MUFU
+#endif
+#ifndef FA_SPLIT_P
+#define FA_SPLIT_P 1     // signal the MMA warp after 3/4 of P so P V starts before the last quarter
+#endif
+
 template <int D>
 struct FwdConfig {
     static constexpr int kBlockM = 128;
@@ -77,7 +89,7 @@ struct FwdConfig {
     static constexpr int kKvStages = (D == 128) ? 4 : 6;
     static constexpr int kSmemQ = 2 * kTileBytes;
     static constexpr int kSmemKV = kKvStages * kTileBytes;
-    static constexpr int kNumBars = 2 + 2 * kKvStages + 2 + 2 + 2 + 2 + 2;
+    static constexpr int kNumBars = 2 + 2 * kKvStages + 2 + 2 + 2 + 2 + 2 + 2;
     static constexpr int kOffBars = kSmemQ + kSmemKV;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
     static constexpr int kOffScale = (kOffTmemPtr + 16 + 15) & ~15;
@@ -180,6 +192,32 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         return;
     }
 
+    // Iterations run over KV tiles in DESCENDING order: iteration `it` handles tile n_max-1-it, so the
+    // masked (diagonal / ragged-tail) tiles come first. Stage s (rows m0+128s ..) only takes part in
+    // iterations [it_lo[s], it_hi[s]): tiles wholly above its causal diagonal or wholly left of its
+    // window are skipped for that stage (the K/V tile is still streamed for the other stage).
+    int it_lo[2], it_hi[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int r0 = m0 + s * BM;
+        int hi_n = n_max, lo_n = n_min;
+        if (r0 >= g.seqlen_q) {
+            hi_n = lo_n = n_min;  // no valid row in this stage
+        } else {
+            if (p.window_right >= 0) {
+                const int max_col = min(r0 + BM, g.seqlen_q) - 1 + off + p.window_right;
+                hi_n = min(n_max, max_col < 0 ? 0 : max_col / BN + 1);
+            }
+            if (p.window_left >= 0) {
+                const int min_col = r0 + off - p.window_left;
+                lo_n = max(n_min, min_col >= 0 ? min_col / BN : 0);
+            }
+            hi_n = max(hi_n, lo_n);
+        }
+        it_lo[s] = n_max - hi_n;
+        it_hi[s] = n_max - lo_n;
+    }
+
     // ------------------------------------------------------------------ shared-memory carve-up
     const uint32_t sQ = sbase;
     const uint32_t sKV = sbase + Cfg::kSmemQ;
@@ -187,11 +225,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     auto bar_q_full = [&](int s) { return bars + 8 * s; };
     auto bar_kv_full = [&](int i) { return bars + 8 * (2 + i); };
     auto bar_kv_empty = [&](int i) { return bars + 8 * (2 + KV + i); };
-    auto bar_s_full = [&](int s) { return bars + 8 * (2 + 2 * KV + s); };
-    auto bar_p_full = [&](int s) { return bars + 8 * (4 + 2 * KV + s); };
-    auto bar_stats = [&](int s) { return bars + 8 * (6 + 2 * KV + s); };
-    auto bar_final = [&](int s) { return bars + 8 * (8 + 2 * KV + s); };
-    auto bar_o_full = [&](int s) { return bars + 8 * (10 + 2 * KV + s); };
+    auto bar_s_full = [&](int s) { return bars + 8 * (2 + 2 * KV + s); };   // MMA -> softmax: S_s ready
+    auto bar_p_full = [&](int s) { return bars + 8 * (4 + 2 * KV + s); };   // softmax+correction -> MMA
+    auto bar_stats = [&](int s) { return bars + 8 * (6 + 2 * KV + s); };    // softmax -> correction: scale
+    auto bar_final = [&](int s) { return bars + 8 * (8 + 2 * KV + s); };    // softmax -> correction: l, m
+    auto bar_o_full = [&](int s) { return bars + 8 * (10 + 2 * KV + s); };  // MMA -> correction: O_s final
+    auto bar_p_last = [&](int s) { return bars + 8 * (12 + 2 * KV + s); };  // softmax -> MMA: last 1/4 of P
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffTmemPtr);
     float* sScale = reinterpret_cast<float*>(sgen + Cfg::kOffScale);
     float* sRowSum = reinterpret_cast<float*>(sgen + Cfg::kOffRowSum);
@@ -205,6 +244,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             mbar_init(bar_stats(s), 4);
             mbar_init(bar_final(s), 4);
             mbar_init(bar_o_full(s), 1);
+            mbar_init(bar_p_last(s), 4);
         }
         for (int i = 0; i < KV; ++i) {
             mbar_init(bar_kv_full(i), 1);
@@ -243,7 +283,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 row = g.k_off + r;
             }
         };
-        int ring = 0;
+        int ring = 0;  // K of iteration it is ring entry 2*it, V is 2*it+1
         auto produce = [&](const CUtensorMap* tm, int n) {
             const int slot = ring % KV;
             const uint32_t parity = ((ring / KV) & 1) ^ 1;
@@ -272,81 +312,58 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         const uint32_t tS[2] = {tmem_base + Cfg::kTmemS0, tmem_base + Cfg::kTmemS1};
         const uint32_t tO[2] = {tmem_base + Cfg::kTmemO0, tmem_base + Cfg::kTmemO1};
 
-        // S_s = Q_s K^T : both operands K-major, 128B swizzle, 8-row groups 1024 B apart.
+        // Descriptor words (ptx_sm100.cuh): lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version | swizzle.
+        // Q, K: K-major, 128B swizzle, 8-row groups 1024 B apart (LBO unused = 1).
+        // V: MN-major B operand: 64-column blocks kHalfBytes apart (LBO), 8-row groups 1024 B apart (SBO).
+        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        constexpr uint32_t kLoKmajor = 1u << 16;
+        constexpr uint32_t kLoVmn = (uint32_t)(Cfg::kHalfBytes >> 4) << 16;
+        auto lo_addr = [](uint32_t saddr) { return (saddr & 0x3FFFFu) >> 4; };
+        // The whole warp stays convergent; each issue block elects one lane (umma_issue_gen.cuh).
         auto issue_qk = [&](int s, uint32_t k_smem) {
-            const uint32_t q_smem = sQ + s * Cfg::kTileBytes;
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-                const uint32_t koff = (kk / 4) * Cfg::kHalfBytes + (kk % 4) * 32;
-                umma_ss(tS[s], umma_desc_sw128(q_smem + koff, 16, 1024),
-                        umma_desc_sw128(k_smem + koff, 16, 1024), idesc_qk, kk > 0 ? 1u : 0u);
-            }
+            const uint32_t a_lo = lo_addr(sQ + s * Cfg::kTileBytes) | kLoKmajor;
+            const uint32_t b_lo = lo_addr(k_smem) | kLoKmajor;
+            if constexpr (D == 128) umma_issue_qk_d128(tS[s], a_lo, b_lo, kDescHi, kDescHi, idesc_qk);
+            else umma_issue_qk_d64(tS[s], a_lo, b_lo, kDescHi, kDescHi, idesc_qk);
         };
-        // O_s (+)= P_s V : A = P from TMEM (16-bit pairs, 8 columns per k-step of 16),
-        // B = V tile [kv rows][head_dim] = MN-major: 64-column blocks kHalfBytes apart (LBO),
-        // 8-row groups 1024 B apart (SBO); a k-step of 16 kv rows advances 2048 B.
-        auto issue_pv = [&](int s, uint32_t v_smem, bool accumulate) {
-            const uint32_t tP = tS[s] + Cfg::kTmemPOff;
-#pragma unroll
-            for (int kk = 0; kk < BN / 16; ++kk) {
-                umma_ts(tO[s], tP + kk * 8, umma_desc_sw128(v_smem + kk * 2048, Cfg::kHalfBytes, 1024),
-                        idesc_pv, (accumulate || kk > 0) ? 1u : 0u);
-            }
-        };
-
-        int ring = 0;
         auto slot_addr = [&](int r) { return sKV + (r % KV) * Cfg::kTileBytes; };
         auto wait_full = [&](int r) { mbar_wait(bar_kv_full(r % KV), (r / KV) & 1); };
 
-        // first K tile: S0, S1
-        wait_full(ring);
         mbar_wait(bar_q_full(0), 0);
-        tc_fence_after();
-        if (lane == 0) {
-            issue_qk(0, slot_addr(ring));
-            umma_commit(bar_s_full(0));
-        }
-        __syncwarp();
-        mbar_wait(bar_q_full(1), 0);
-        tc_fence_after();
-        if (lane == 0) {
-            issue_qk(1, slot_addr(ring));
-            umma_commit(bar_s_full(1));
-            umma_commit(bar_kv_empty(ring % KV));
-        }
-        __syncwarp();
-        ++ring;
-
-        for (int it = 1; it < n_tiles; ++it) {
-            const int rv = ring, rk = ring + 1;  // V_{it-1}, K_it
-            wait_full(rv);
+        // Issue order per iteration: PV0(it-1) QK0(it) PV1(it-1) QK1(it). tcgen05 ops execute in issue
+        // order, so S_s(it) may overwrite the columns P_s(it-1) lives in without a barrier.
+        for (int it = 0; it <= n_tiles; ++it) {
+            if (it > 0) wait_full(2 * it - 1);
+            if (it < n_tiles) wait_full(2 * it);
+            if (it == 0) mbar_wait(bar_q_full(1), 0);
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                mbar_wait(bar_p_full(s), (it - 1) & 1);
-                if (s == 0) wait_full(rk);
-                tc_fence_after();
-                if (lane == 0) {
-                    issue_pv(s, slot_addr(rv), it > 1);
-                    if (s == 1) umma_commit(bar_kv_empty(rv % KV));
-                    issue_qk(s, slot_addr(rk));
-                    umma_commit(bar_s_full(s));
-                    if (s == 1) umma_commit(bar_kv_empty(rk % KV));
+                const bool do_pv = it > 0 && (it - 1) >= it_lo[s] && (it - 1) < it_hi[s];
+                const bool do_qk = it < n_tiles && it >= it_lo[s] && it < it_hi[s];
+                if (do_pv) {
+                    const int j = it - 1 - it_lo[s];
+                    const uint32_t tP = tS[s] + Cfg::kTmemPOff;
+                    const uint32_t v_lo = lo_addr(slot_addr(2 * it - 1)) | kLoVmn;
+                    mbar_wait(bar_p_full(s), j & 1);
+                    tc_fence_after();
+                    if (FA_SPLIT_P) {
+                        umma_issue_pv_k0_6(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, j > 0 ? 1u : 0u);
+                        mbar_wait(bar_p_last(s), j & 1);
+                        tc_fence_after();
+                        umma_issue_pv_k6_8(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, 1u);
+                    } else {
+                        umma_issue_pv_k0_8(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, j > 0 ? 1u : 0u);
+                    }
+                    if (it == it_hi[s]) umma_commit_elect(bar_o_full(s));
                 }
-                __syncwarp();
+                if (do_qk) {
+                    tc_fence_after();
+                    issue_qk(s, slot_addr(2 * it));
+                    umma_commit_elect(bar_s_full(s));
+                }
             }
-            ring += 2;
-        }
-        // last V tile
-        wait_full(ring);
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            mbar_wait(bar_p_full(s), (n_tiles - 1) & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                issue_pv(s, slot_addr(ring), n_tiles > 1);
-                umma_commit(bar_o_full(s));
-            }
-            __syncwarp();
+            if (it > 0) umma_commit_elect(bar_kv_empty((2 * it - 1) % KV));
+            if (it < n_tiles) umma_commit_elect(bar_kv_empty((2 * it) % KV));
         }
     } else if (warp < 8) {
         // ============================================================ softmax (stage = warp / 4)
@@ -357,6 +374,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         const uint32_t tS = tmem_base + lane_off + (s == 0 ? Cfg::kTmemS0 : Cfg::kTmemS1);
         const uint32_t tP = tS + Cfg::kTmemPOff;
         const int i_glob = m0 + s * BM + row;  // row index inside the sequence
+        const int my_lo = s == 0 ? it_lo[0] : it_lo[1];
+        const int my_n = (s == 0 ? it_hi[0] : it_hi[1]) - my_lo;
 
         // visible key range of this row: [col_lo, col_hi)
         int col_hi = g.seqlen_k;
@@ -375,9 +394,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         float m_ref = -INFINITY;  // running reference max (raw score units; log2 units if FEAT)
         float row_sum = 0.f;
 
-        for (int it = 0; it < n_tiles; ++it) {
-            const int j0 = (n_max - 1 - it) * BN;
-            mbar_wait(bar_s_full(s), it & 1);
+        for (int j = 0; j < my_n; ++j) {
+            const int j0 = (n_max - 1 - (my_lo + j)) * BN;
+            mbar_wait(bar_s_full(s), j & 1);
             tc_fence_after();
             float v[BN];
             tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
@@ -401,18 +420,20 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     v[c] = ((unsigned)(base + c) < col_width) ? v[c] : -INFINITY;
             }
 
-            float mx0 = fmax3(v[0], v[1], v[2]), mx1 = fmax3(v[3], v[4], v[5]);
+            // row max: four independent 3-input max chains
+            float mx[4];
 #pragma unroll
-            for (int c = 6; c + 3 < BN; c += 4) {
-                mx0 = fmax3(mx0, v[c], v[c + 1]);
-                mx1 = fmax3(mx1, v[c + 2], v[c + 3]);
+            for (int a = 0; a < 4; ++a) mx[a] = fmaxf(v[2 * a], v[2 * a + 1]);
+#pragma unroll
+            for (int c = 8; c < BN; c += 8) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) mx[a] = fmax3(mx[a], v[c + 2 * a], v[c + 2 * a + 1]);
             }
-            mx0 = fmax3(mx0, v[BN - 2], v[BN - 1]);
-            const float m_new = fmaxf(m_ref, fmaxf(mx0, mx1));
+            const float m_new = fmaxf(m_ref, fmax3(fmaxf(mx[0], mx[1]), mx[2], mx[3]));
             const float m_new_safe = (m_new == -INFINITY) ? 0.f : m_new;
 
             float acc_scale = 1.0f;
-            if (it == 0) {
+            if (j == 0) {
                 m_ref = m_new;
             } else {
                 const float d = (m_ref - m_new_safe) * sl2;  // <= 0, -inf if nothing was visible yet
@@ -433,18 +454,29 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int c = 0; c < 32; c += 2) {
-                    const float p0 = ex2_approx(fmaf(v[ch * 32 + c], sl2, neg_m));
-                    const float p1 = ex2_approx(fmaf(v[ch * 32 + c + 1], sl2, neg_m));
-                    sum0 += p0;
-                    sum1 += p1;
+                    float p0 = v[ch * 32 + c], p1 = v[ch * 32 + c + 1];
+                    fma2(p0, p1, sl2, sl2, neg_m, neg_m);
+                    if (FA_EMU_COUNT > 0 && ((c / 2) % FA_EMU_PERIOD) >= FA_EMU_PERIOD - FA_EMU_COUNT) {
+                        ex2_emu2(p0, p1);
+                    } else {
+                        p0 = ex2_approx(p0);
+                        p1 = ex2_approx(p1);
+                    }
+                    add2(sum0, sum1, p0, p1);
                     pk[c / 2] = pack2<BF16>(p0, p1);
                 }
                 tmem_st_x16(tP + ch * 16, pk);
+                if (FA_SPLIT_P && ch == BN / 32 - 2) {  // 3/4 of P is on its way: let P V start
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_p_full(s));
+                }
             }
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_p_full(s));
+            if (lane == 0) mbar_arrive(FA_SPLIT_P ? bar_p_last(s) : bar_p_full(s));
             row_sum = row_sum * acc_scale + (sum0 + sum1);
         }
         sRowSum[s * BM + row] = row_sum;
@@ -461,9 +493,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         for (int it = 0; it < n_tiles; ++it) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                mbar_wait(bar_stats(s), it & 1);
+                if (it < it_lo[s] || it >= it_hi[s]) continue;
+                const int j = it - it_lo[s];
+                mbar_wait(bar_stats(s), j & 1);
                 const float sc = sScale[s * BM + row];
-                if (it > 0 && __any_sync(0xffffffffu, sc != 1.0f)) {
+                if (j > 0 && __any_sync(0xffffffffu, sc != 1.0f)) {
                     tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < D / 32; ++c) {
@@ -484,16 +518,25 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         uint16_t* outp = reinterpret_cast<uint16_t*>(p.out);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
+            const int i_glob = m0 + s * BM + row;
+            const bool valid = i_glob < g.seqlen_q;
+            uint16_t* dst = outp + o_b * p.o_stride_b + (int64_t)(g.q_off + i_glob) * p.o_stride_s +
+                            head * p.o_stride_h;
+            float* lse_dst = p.lse + o_b * p.lse_stride_b + head * p.lse_stride_h + g.q_off + i_glob;
+            if (it_hi[s] <= it_lo[s]) {  // this stage saw no KV tile: no key is visible to its rows
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
+                    *lse_dst = kNegSentinel;
+                }
+                continue;
+            }
             mbar_wait(bar_final(s), 0);
             const float l = sRowSum[s * BM + row];
             const float mx = sRowMax[s * BM + row];
             mbar_wait(bar_o_full(s), 0);
             tc_fence_after();
-            const int i_glob = m0 + s * BM + row;
-            const bool valid = i_glob < g.seqlen_q;
             const float inv = l > 0.f ? 1.0f / l : 0.f;
-            uint16_t* dst = outp + o_b * p.o_stride_b + (int64_t)(g.q_off + i_glob) * p.o_stride_s +
-                            head * p.o_stride_h;
 #pragma unroll
             for (int c = 0; c < D / 32; ++c) {
                 float o[32];
@@ -510,10 +553,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     }
                 }
             }
-            if (valid) {
-                const float lse = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : kNegSentinel;
-                p.lse[o_b * p.lse_stride_b + head * p.lse_stride_h + g.q_off + i_glob] = lse;
-            }
+            if (valid) *lse_dst = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : kNegSentinel;
         }
     } else {
         reg_dec<48>();  // warps 14, 15: spare

@@ -207,6 +207,51 @@ FA_DEVICE float fmax3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
     return y;
 }
+// ---------------------------------------------------------------- packed fp32x2 math (FFMA2 / FADD2)
+// a = a * s + b  on two lanes at once
+FA_DEVICE void fma2(float& a0, float& a1, float s0, float s1, float b0, float b1) {
+    asm("{\n\t.reg .b64 x, y, z;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tmov.b64 z, {%4, %5};\n\t"
+        "fma.rn.f32x2 x, x, y, z;\n\tmov.b64 {%0, %1}, x;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(s0), "f"(s1), "f"(b0), "f"(b1));
+}
+FA_DEVICE void add2(float& a0, float& a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\t"
+        "add.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
+FA_DEVICE void add2_rm(float& a0, float& a1, float b0, float b1) {  // round toward -inf
+    asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\t"
+        "add.rm.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
+
+// 2^x for a pair, evaluated on the FMA/ALU pipes instead of the MUFU (which is the scarcest pipe of
+// the softmax: 16 ex2/clk/SM against 8192 tensor FLOP/clk/SM).  Cody-Waite split with the
+// 1.5*2^23 magic constant: r = x + magic rounded DOWN holds floor(x) in its low mantissa bits,
+// f = x - floor(x) in [0,1), 2^f by a degree-3 polynomial (max rel. error 8.6e-5, well below the
+// 2^-9 / 2^-11 rounding of the 16-bit P it feeds), and floor(x) is added into the exponent field
+// with one integer shift-add.  Inputs below -127 (masked / negligible) are clamped and give 0.
+FA_DEVICE void ex2_emu2(float& x0, float& x1) {
+    constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+    constexpr float c1 = 0.6951165795326233f, c2 = 0.22764593362808228f, c3 = 0.07706617563962936f;
+    x0 = fmaxf(x0, -127.0f);
+    x1 = fmaxf(x1, -127.0f);
+    float r0 = x0, r1 = x1;
+    add2_rm(r0, r1, kMagic, kMagic);
+    float f0 = r0, f1 = r1;
+    add2(f0, f1, -kMagic, -kMagic);      // floor(x) as a float
+    fma2(f0, f1, -1.0f, -1.0f, x0, x1);  // f = x - floor(x)
+    float p0 = c3, p1 = c3;
+    fma2(p0, p1, f0, f1, c2, c2);
+    fma2(p0, p1, f0, f1, c1, c1);
+    fma2(p0, p1, f0, f1, 1.0f, 1.0f);
+    x0 = __int_as_float((__float_as_int(r0) << 23) + __float_as_int(p0));
+    x1 = __int_as_float((__float_as_int(r1) << 23) + __float_as_int(p1));
+}
+
 // pack two fp32 into one 32-bit register holding (lo, hi) 16-bit floats, round-to-nearest-even
 template <bool BF16>
 FA_DEVICE uint32_t pack2(float lo, float hi) {

@@ -196,7 +196,7 @@ def fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, windo
 
     lse = torch.empty((B, H, M), dtype=torch.float32, device=q.device)
     dmask = torch.empty((0,), dtype=q.dtype, device=q.device)
-    rng_state = torch.zeros((2,), dtype=torch.int64, device=q.device)
+    rng_state = torch.empty((2,), dtype=torch.int64, device=q.device)  # only meaningful with dropout
     if out_ is not None:
         _check(out_.dtype == q.dtype, "out must have the same dtype as q")
         _check(out_.is_cuda, "out must be on CUDA")
@@ -276,7 +276,7 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k_, leftpad_k_
 
     lse = torch.empty((H, T), dtype=torch.float32, device=q.device)
     dmask = torch.empty((0,), dtype=q.dtype, device=q.device)
-    rng_state = torch.zeros((2,), dtype=torch.int64, device=q.device)
+    rng_state = torch.empty((2,), dtype=torch.int64, device=q.device)  # only meaningful with dropout
     if out_ is not None:
         _check(out_.dtype == q.dtype and out_.is_cuda and out_.stride(-1) == 1 and out_.shape == q.shape,
                "out must match q in dtype, device and shape with a contiguous last dimension")

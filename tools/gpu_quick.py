@@ -52,23 +52,26 @@ def run_case(name, B, Sq, Sk, H, Hk, D, dtype, causal, window=(-1, -1), softcap=
     results.append(rec)
 
 
-def bench_case(name, B, S, H, Hk, D, dtype, causal, iters=10):
+def bench_case(name, B, S, H, Hk, D, dtype, causal, iters=10, window=(-1, -1)):
     dev = "cuda"
     torch.manual_seed(421)
     q = torch.randn(B, S, H, D, device=dev, dtype=dtype)
     k = torch.randn(B, S, Hk, D, device=dev, dtype=dtype)
     v = torch.randn(B, S, Hk, D, device=dev, dtype=dtype)
     for _ in range(3):
-        flash_attn_func(q, k, v, causal=causal)
+        flash_attn_func(q, k, v, causal=causal, window_size=window)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        flash_attn_func(q, k, v, causal=causal)
+        flash_attn_func(q, k, v, causal=causal, window_size=window)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     flops = 4 * B * H * S * S * D * (0.5 if causal else 1.0)
+    if window[0] >= 0:
+        w = window[0]
+        flops = 4 * B * H * D * (w * (w + 1) // 2 + (S - w) * (w + 1))
     rec = {"name": name, "ms": ms, "tflops": flops / ms / 1e9}
     print(json.dumps(rec), flush=True)
     results.append(rec)
@@ -87,10 +90,15 @@ if __name__ == "__main__":
     run_case("d128_bf16_softcap", 1, 512, 512, 2, 2, 128, bf16, False, softcap=30.0)
     run_case("d128_bf16_alibi", 1, 512, 512, 2, 2, 128, bf16, True, alibi=True)
     run_case("d128_bf16_causal_2048_gqa", 1, 2048, 2048, 8, 2, 128, bf16, True)
+    tag = sys.argv[1] if len(sys.argv) > 1 else "default"
     if all(r.get("ok") for r in results):
-        bench_case("C2_bf16_B8_H32_S4096_D128_causal", 8, 4096, 32, 32, 128, bf16, True)
+        bench_case("C2_bf16_B8_H32_S4096_D128_causal", 8, 4096, 32, 32, 128, bf16, True, iters=20)
         bench_case("bf16_B8_H32_S4096_D128_full", 8, 4096, 32, 32, 128, bf16, False)
+        bench_case("C2gqa_bf16_B8_H32_Hk8_S4096_causal", 8, 4096, 32, 8, 128, bf16, True, iters=20)
+        bench_case("C5shard_bf16_B8_H32_S8192_win4096", 8, 8192, 32, 32, 128, bf16, True, window=(4096, 0))
+        bench_case("bf16_B4_H32_S16384_D128_causal", 4, 16384, 32, 32, 128, bf16, True, iters=5)
+        bench_case("f16_B8_H32_S4096_D64_causal", 8, 4096, 32, 32, 64, f16, True)
         bench_case("C1_f16_B2_H8_S512_D64_full", 2, 512, 8, 8, 64, f16, False)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(results, open(os.path.join(ROOT, "gpurun_out", "quick.json"), "w"), indent=1)
+    json.dump(results, open(os.path.join(ROOT, "gpurun_out", f"quick_{tag}.json"), "w"), indent=1)
     print("elapsed", time.time() - t0)
