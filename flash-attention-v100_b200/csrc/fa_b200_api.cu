@@ -59,7 +59,8 @@ EncodeTiledFn get_encode_fn() {
 // 4-D view (head_dim, heads, rows, batch) of a 16-bit tensor with unit head_dim stride;
 // box = 64 x 1 x 128 x 1 with the 128-byte swizzle the UMMA descriptors expect.
 int make_tmap(CUtensorMap* tm, int dtype, const void* ptr, int head_dim, int64_t heads, int64_t rows,
-              int64_t batch, int64_t stride_h, int64_t stride_s, int64_t stride_b, const char* name) {
+              int64_t batch, int64_t stride_h, int64_t stride_s, int64_t stride_b, const char* name,
+              int box_heads = 1, int box_rows = 128) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA_B200_EARCH, "cuTensorMapEncodeTiled is not available from this driver");
     CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s must be 16-byte aligned", name);
@@ -69,7 +70,7 @@ int make_tmap(CUtensorMap* tm, int dtype, const void* ptr, int head_dim, int64_t
                           (cuuint64_t)(batch > 0 ? batch : 1)};
     auto nz = [](int64_t s) { return (cuuint64_t)((s > 0 ? s : 8) * 2); };
     cuuint64_t strides[3] = {nz(stride_h), nz(stride_s), nz(stride_b)};
-    cuuint32_t box[4] = {64, 1, 128, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_heads, (cuuint32_t)box_rows, 1};  // box_heads * box_rows == 128 tile rows
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(tm, dtype == FA_B200_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                      4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -94,10 +95,10 @@ int check_device(int device) {
     return 0;
 }
 
-template <int D, bool BF16, bool FEAT>
+template <int D, bool BF16, bool FEAT, bool DECODE = false>
 int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
     using Cfg = fa::FwdConfig<D>;
-    auto kern = fa::fa_fwd_sm100_kernel<D, BF16, FEAT>;
+    auto kern = fa::fa_fwd_sm100_kernel<D, BF16, FEAT, DECODE>;
     static std::once_flag once[64];
     int dev = 0;
     cudaGetDevice(&dev);
@@ -127,6 +128,73 @@ int launch_fwd(const fa::FwdKernelParams& kp, int head_dim, int dtype, bool feat
     FA_CASE(64, false, true)
 #undef FA_CASE
     return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (64 and 128 are)", head_dim);
+}
+
+// Decode path: packed-GQA split-KV launch + combine.
+int launch_decode(const fa::FwdKernelParams& kp, int head_dim, int dtype, dim3 grid, cudaStream_t stream) {
+    const bool bf16 = dtype == FA_B200_DTYPE_BF16;
+    if (head_dim == 128 && bf16) return launch_fwd_t<128, true, false, true>(kp, grid, stream);
+    if (head_dim == 128 && !bf16) return launch_fwd_t<128, false, false, true>(kp, grid, stream);
+    if (head_dim == 64 && bf16) return launch_fwd_t<64, true, false, true>(kp, grid, stream);
+    if (head_dim == 64 && !bf16) return launch_fwd_t<64, false, false, true>(kp, grid, stream);
+    return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (64 and 128 are)", head_dim);
+}
+
+int launch_combine(const fa::FwdKernelParams& kp, const fa_b200_params_t* p, cudaStream_t stream) {
+    const int64_t rows = (int64_t)p->batch * p->num_heads * p->seqlen_q;
+    const int warps = 4;
+    const dim3 grid((unsigned)((rows + warps - 1) / warps));
+    uint16_t* out = static_cast<uint16_t*>(p->out);
+    const bool bf16 = p->dtype == FA_B200_DTYPE_BF16;
+#define FA_COMBINE(DD, BB)                                                                                   \
+    fa::fa_combine_kernel<DD, BB><<<grid, warps * 32, 0, stream>>>(kp.o_partial, kp.lse_partial, out, p->lse, \
+        kp.num_splits, p->batch, p->num_heads, p->seqlen_q, p->o_stride_b, p->o_stride_s, p->o_stride_h)
+    if (p->head_dim == 128 && bf16) FA_COMBINE(128, true);
+    else if (p->head_dim == 128) FA_COMBINE(128, false);
+    else if (bf16) FA_COMBINE(64, true);
+    else FA_COMBINE(64, false);
+#undef FA_COMBINE
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fa_combine_kernel launch");
+    return 0;
+}
+
+// Decode applies when a whole GQA group's query rows fit one 128-row tile and no score modifier is on.
+bool decode_applies(const fa_b200_params_t* p) {
+    const int G = p->num_heads / p->num_heads_k;
+    if (G > 128 || (G & (G - 1)) != 0) return false;
+    if ((int64_t)p->seqlen_q * G > 128) return false;
+    return p->alibi_slopes == nullptr && p->softcap == 0.f;
+}
+
+// KV splits per (batch, kv head): fill the 148 SMs for several waves but keep >= 4 tiles per split.
+int decode_num_splits(const fa_b200_params_t* p) {
+    if (p->num_splits == 1) return 1;
+    const int tiles = (p->seqlen_k + 127) / 128;
+    const int64_t base = (int64_t)p->batch * p->num_heads_k;
+    int best = 1;
+    double best_score = 0.0;
+    for (int s = 1; s <= 64 && s * 4 <= (tiles > 4 ? tiles : 4); ++s) {
+        const int64_t ctas = base * s;
+        const double waves = (double)ctas / 148.0;
+        const double eff = waves / (double)((ctas + 147) / 148);      // wave quantisation
+        const double per = (double)((tiles + s - 1) / s);
+        const double score = eff * per / (per + 1.5);                  // ~1.5 tiles of fixed cost per CTA
+        if (score > best_score * 1.02) {
+            best_score = score;
+            best = s;
+        }
+    }
+    return best;
+}
+
+int64_t decode_workspace_bytes(const fa_b200_params_t* p) {
+    if (!decode_applies(p)) return 0;
+    const int s = decode_num_splits(p);
+    if (s <= 1) return 0;
+    const int64_t rows = (int64_t)s * p->batch * p->num_heads * p->seqlen_q;
+    return ((rows * p->head_dim * 4 + 255) & ~(int64_t)255) + ((rows * 4 + 255) & ~(int64_t)255);
 }
 
 struct DeviceGuard {
@@ -195,6 +263,7 @@ FA_B200_API int64_t fa_b200_workspace_bytes(const fa_b200_params_t* p, int kind)
     if (p->rotary_dim > 0)  // rotated copy of q
         bytes += (int64_t)p->batch * p->seqlen_q * p->num_heads * p->head_dim * 2;
     bytes = (bytes + 255) & ~(int64_t)255;
+    bytes += decode_workspace_bytes(p);
     return bytes;
 }
 
@@ -399,6 +468,7 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
     // 3. attention over the cache: the tcgen05 kernel reading the (paged) cache through TMA
     fa::FwdKernelParams kp;
     fill_common(kp, p, causal, wl, wr);
+    const bool decode = decode_applies(p);
     kp.seqlen_q = p->seqlen_q;
     kp.seqlen_k = p->seqlen_k;
     kp.cache_seqlens = p->cache_seqlens;
@@ -410,11 +480,30 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
     kp.page_size = p->page_size;
     kp.lse_stride_b = (int64_t)p->num_heads * p->seqlen_q;
     kp.lse_stride_h = p->seqlen_q;
-    if (int rc = make_tmap(&kp.tm_q, p->dtype, q_ptr, p->head_dim, p->num_heads, p->seqlen_q, p->batch, q_sh, q_ss, q_sb, "q")) return rc;
+    const int G = p->num_heads / p->num_heads_k;
+    if (int rc = make_tmap(&kp.tm_q, p->dtype, q_ptr, p->head_dim, p->num_heads, p->seqlen_q, p->batch, q_sh, q_ss, q_sb, "q",
+                           decode ? G : 1, decode ? 128 / G : 128)) return rc;
     const int64_t rows = paged ? p->page_size : p->seqlen_k;
     const int64_t nb = paged ? p->num_pages : p->batch_k;
     if (int rc = make_tmap(&kp.tm_k, p->dtype, p->k, p->head_dim, p->num_heads_k, rows, nb, p->k_stride_h, p->k_stride_s, p->k_stride_b, "k_cache")) return rc;
     if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, rows, nb, p->v_stride_h, p->v_stride_s, p->v_stride_b, "v_cache")) return rc;
+    if (decode) {
+        // few query rows: pack the GQA group into the tile rows and split the KV length over CTAs
+        kp.gqa_pack = G;
+        kp.num_splits = decode_num_splits(p);
+        if (kp.num_splits > 1) {
+            const int64_t prow = (int64_t)kp.num_splits * p->batch * p->num_heads * p->seqlen_q;
+            const int64_t obytes = (prow * p->head_dim * 4 + 255) & ~(int64_t)255;
+            const int64_t lbytes = (prow * 4 + 255) & ~(int64_t)255;
+            CHECK_ARG(ws != nullptr && ws_left >= obytes + lbytes, "workspace too small for %d KV splits (see fa_b200_workspace_bytes)", kp.num_splits);
+            kp.o_partial = reinterpret_cast<float*>(ws);
+            kp.lse_partial = reinterpret_cast<float*>(ws + obytes);
+        }
+        dim3 grid(kp.num_splits, p->num_heads_k, p->batch);
+        if (int rc = launch_decode(kp, p->head_dim, p->dtype, grid, stream)) return rc;
+        if (kp.num_splits > 1) return launch_combine(kp, p, stream);
+        return 0;
+    }
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
     dim3 grid((p->seqlen_q + 255) / 256, p->num_heads, p->batch);
     return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);

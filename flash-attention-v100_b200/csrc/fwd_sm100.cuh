@@ -62,6 +62,11 @@ struct alignas(64) FwdKernelParams {
     int window_left;   // -1 = unbounded
     int window_right;  // -1 = unbounded; causal is window_right = 0
     int reverse_m;     // launch the longest query blocks first (causal / local)
+    // decode mode (packed GQA + split-KV): the 128 tile rows are (query position, head-in-group) pairs
+    int gqa_pack;        // query heads per KV head packed into the row dimension
+    int num_splits;      // CTAs along the KV length per (batch, kv head); > 1 => partial results
+    float* o_partial;    // [split][batch][head][seqlen_q][D] fp32, normalised per split
+    float* lse_partial;  // [split][batch][head][seqlen_q] fp32, -inf for an empty split
 };
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -138,7 +143,11 @@ FA_DEVICE SeqGeom load_geom(const FwdKernelParams& p, int batch) {
     return g;
 }
 
-template <int D, bool BF16, bool FEAT>
+// DECODE = false: grid (query blocks of 256 rows, query heads, batch); two query tiles per CTA.
+// DECODE = true : grid (KV splits, KV heads, batch); ONE tile whose 128 rows are the (position, head)
+//                 pairs of a whole GQA group (row = position * G + head_in_group), so a decode step reads
+//                 each K/V byte once per group; only stage 0 runs. HBM-bound by construction.
+template <int D, bool BF16, bool FEAT, bool DECODE = false>
 __global__ void __launch_bounds__(512, 1)
 fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     using Cfg = FwdConfig<D>;
@@ -153,19 +162,22 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int m_block = p.reverse_m ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-    const int head = blockIdx.y;
+    const int G = DECODE ? p.gqa_pack : 1;
+    const int m_block = DECODE ? 0 : (p.reverse_m ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x);
+    const int split = DECODE ? (int)blockIdx.x : 0;
+    const int head = DECODE ? (int)blockIdx.y * G : (int)blockIdx.y;  // first query head of the group
     const int batch = blockIdx.z;
     const SeqGeom g = load_geom(p, batch);
     const int m0 = m_block * (2 * BM);
     if (m0 >= g.seqlen_q) return;  // over-provisioned varlen grid
+    // query positions covered by this CTA: [m0, m_end)
+    const int m_end = DECODE ? g.seqlen_q : min(m0 + 2 * BM, g.seqlen_q);
 
-    // KV tile range [n_min, n_max) visible to this 256-row query block (bottom-right aligned).
+    // KV tile range [n_min, n_max) visible to these query rows (bottom-right aligned).
     const int off = g.seqlen_k - g.seqlen_q;
     int n_max = (g.seqlen_k + BN - 1) / BN;
     if (p.window_right >= 0) {
-        const int last_row = min(m0 + 2 * BM, g.seqlen_q) - 1;
-        const int max_col = last_row + off + p.window_right;
+        const int max_col = m_end - 1 + off + p.window_right;
         n_max = min(n_max, max_col < 0 ? 0 : max_col / BN + 1);
     }
     int n_min = 0;
@@ -173,22 +185,37 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         const int min_col = m0 + off - p.window_left;
         n_min = max(0, min_col >= 0 ? min_col / BN : 0);
     }
+    if constexpr (DECODE) {  // this CTA's share of the KV tiles
+        const int per = (max(n_max - n_min, 0) + p.num_splits - 1) / p.num_splits;
+        const int lo = n_min + split * per;
+        n_max = min(n_max, lo + per);
+        n_min = min(lo, n_max);
+    }
     const int n_tiles = n_max - n_min;
     const int o_b = p.cu_seqlens_q ? 0 : batch;
+    const bool partial_out = DECODE && p.num_splits > 1;
 
     if (n_tiles <= 0) {
         // No visible key for any row of this block: out = 0, lse = sentinel
-        // (reference kernel/fused_mha_forward_varlen.cu:100-111).
-        const int rows = min(2 * BM, g.seqlen_q - m0);
+        // (reference kernel/fused_mha_forward_varlen.cu:100-111). A decode split with no tile writes an
+        // ignorable partial (lse = -inf).
+        const int rows = (m_end - m0) * G;  // packed rows: position-major, head-in-group minor
+        if (partial_out) {
+            for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+                const int pos = r / G, h = head + r % G;
+                p.lse_partial[(((int64_t)split * gridDim.z + batch) * p.num_heads + h) * g.seqlen_q + pos] = -INFINITY;
+            }
+            return;
+        }
         uint16_t* outp = reinterpret_cast<uint16_t*>(p.out);
         for (int idx = threadIdx.x; idx < rows * (D / 8); idx += blockDim.x) {
             const int r = idx / (D / 8), c = idx % (D / 8);
-            uint16_t* dst = outp + o_b * p.o_stride_b + (int64_t)(g.q_off + m0 + r) * p.o_stride_s +
-                            head * p.o_stride_h + c * 8;
+            const int pos = m0 + r / G, h = head + r % G;
+            uint16_t* dst = outp + o_b * p.o_stride_b + (int64_t)(g.q_off + pos) * p.o_stride_s + h * p.o_stride_h + c * 8;
             *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
         }
         for (int r = threadIdx.x; r < rows; r += blockDim.x)
-            p.lse[o_b * p.lse_stride_b + head * p.lse_stride_h + g.q_off + m0 + r] = kNegSentinel;
+            p.lse[o_b * p.lse_stride_b + (head + r % G) * p.lse_stride_h + g.q_off + m0 + r / G] = kNegSentinel;
         return;
     }
 
@@ -201,7 +228,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     for (int s = 0; s < 2; ++s) {
         const int r0 = m0 + s * BM;
         int hi_n = n_max, lo_n = n_min;
-        if (r0 >= g.seqlen_q) {
+        if (DECODE) {
+            if (s == 1) hi_n = lo_n = n_min;  // single tile of packed rows: stage 1 is idle
+        } else if (r0 >= g.seqlen_q) {
             hi_n = lo_n = n_min;  // no valid row in this stage
         } else {
             if (p.window_right >= 0) {
@@ -261,7 +290,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int kv_head = head / p.heads_per_kv;
+    const int kv_head = DECODE ? (int)blockIdx.y : head / p.heads_per_kv;
 
     if (warp == 13) {
         // ============================================================ TMA producer
@@ -295,9 +324,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             }
             ++ring;
         };
+        // DECODE: tm_q's box is (64, G, 128/G, 1), so one load brings the G heads of 128/G positions
         if (lane == 0) load_tile(&p.tm_q, sQ, bar_q_full(0), head, g.q_off + m0, g.q_b);
         produce(&p.tm_k, n_max - 1);
-        if (lane == 0)
+        if (!DECODE && lane == 0)
             load_tile(&p.tm_q, sQ + Cfg::kTileBytes, bar_q_full(1), head, g.q_off + m0 + BM, g.q_b);
         produce(&p.tm_v, n_max - 1);
         for (int it = 1; it < n_tiles; ++it) {
@@ -335,7 +365,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         for (int it = 0; it <= n_tiles; ++it) {
             if (it > 0) wait_full(2 * it - 1);
             if (it < n_tiles) wait_full(2 * it);
-            if (it == 0) mbar_wait(bar_q_full(1), 0);
+            if (!DECODE && it == 0) mbar_wait(bar_q_full(1), 0);
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const bool do_pv = it > 0 && (it - 1) >= it_lo[s] && (it - 1) < it_hi[s];
@@ -373,7 +403,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tmem_base + lane_off + (s == 0 ? Cfg::kTmemS0 : Cfg::kTmemS1);
         const uint32_t tP = tS + Cfg::kTmemPOff;
-        const int i_glob = m0 + s * BM + row;  // row index inside the sequence
+        const int i_glob = DECODE ? row / G : m0 + s * BM + row;  // query position inside the sequence
         const int my_lo = s == 0 ? it_lo[0] : it_lo[1];
         const int my_n = (s == 0 ? it_hi[0] : it_hi[1]) - my_lo;
 
@@ -387,7 +417,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         const float sl2 = FEAT ? 1.0f : p.scale_log2;
         float slope = 0.f, inv_cap = 0.f;
         if constexpr (FEAT) {
-            if (p.alibi) slope = p.alibi[batch * p.alibi_stride_b + head];
+            if (p.alibi) slope = p.alibi[batch * p.alibi_stride_b + head + (DECODE ? row % G : 0)];
             if (p.softcap > 0.f) inv_cap = 1.0f / p.softcap;
         }
 
@@ -518,11 +548,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         uint16_t* outp = reinterpret_cast<uint16_t*>(p.out);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            const int i_glob = m0 + s * BM + row;
+            if (DECODE && s == 1) continue;  // packed-row mode has a single tile
+            const int i_glob = DECODE ? row / G : m0 + s * BM + row;
+            const int h_row = DECODE ? head + row % G : head;
             const bool valid = i_glob < g.seqlen_q;
             uint16_t* dst = outp + o_b * p.o_stride_b + (int64_t)(g.q_off + i_glob) * p.o_stride_s +
-                            head * p.o_stride_h;
-            float* lse_dst = p.lse + o_b * p.lse_stride_b + head * p.lse_stride_h + g.q_off + i_glob;
+                            h_row * p.o_stride_h;
+            float* lse_dst = p.lse + o_b * p.lse_stride_b + h_row * p.lse_stride_h + g.q_off + i_glob;
             if (it_hi[s] <= it_lo[s]) {  // this stage saw no KV tile: no key is visible to its rows
                 if (valid) {
 #pragma unroll
@@ -537,6 +569,23 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             mbar_wait(bar_o_full(s), 0);
             tc_fence_after();
             const float inv = l > 0.f ? 1.0f / l : 0.f;
+            if (partial_out) {
+                // split-KV partial: normalised fp32 O and this split's LSE; fa_combine_kernel merges them
+                const int64_t prow = (((int64_t)split * gridDim.z + batch) * p.num_heads + h_row) * g.seqlen_q + i_glob;
+#pragma unroll
+                for (int c = 0; c < D / 32; ++c) {
+                    float o[32];
+                    tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
+                    if (valid) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            *reinterpret_cast<float4*>(p.o_partial + prow * D + c * 32 + e) =
+                                make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
+                    }
+                }
+                if (valid) p.lse_partial[prow] = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : -INFINITY;
+                continue;
+            }
 #pragma unroll
             for (int c = 0; c < D / 32; ++c) {
                 float o[32];
@@ -563,6 +612,43 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     tc_fence_before();
     __syncthreads();
     if (warp == 12) tmem_dealloc<512>(tmem_base);
+}
+
+// Merge the split-KV partials of the decode path: out = sum_i w_i O_i / sum_i w_i with
+// w_i = exp(lse_i - max lse), lse = max + ln(sum w_i). One warp per (batch, head, position) row.
+template <int D, bool BF16>
+__global__ void fa_combine_kernel(const float* __restrict__ o_partial, const float* __restrict__ lse_partial,
+                                  uint16_t* __restrict__ out, float* __restrict__ lse, int num_splits, int batch,
+                                  int heads, int seqlen_q, int64_t o_stride_b, int64_t o_stride_s,
+                                  int64_t o_stride_h) {
+    const int lane = threadIdx.x & 31;
+    const int64_t rows = (int64_t)batch * heads * seqlen_q;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int pos = row % seqlen_q, h = (row / seqlen_q) % heads, b = row / ((int64_t)seqlen_q * heads);
+    float mx = -INFINITY;
+    for (int i = 0; i < num_splits; ++i) mx = fmaxf(mx, lse_partial[(int64_t)i * rows + row]);
+    constexpr int E = D / 32;  // elements per lane
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    float wsum = 0.f;
+    if (mx > -INFINITY) {
+        for (int i = 0; i < num_splits; ++i) {
+            const float w = __expf(lse_partial[(int64_t)i * rows + row] - mx);
+            if (w > 0.f) {
+                const float* src = o_partial + ((int64_t)i * rows + row) * D + lane * E;
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[e] += w * src[e];
+                wsum += w;
+            }
+        }
+    }
+    const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
+    uint16_t* dst = out + b * o_stride_b + (int64_t)pos * o_stride_s + h * o_stride_h + lane * E;
+#pragma unroll
+    for (int e = 0; e < E; e += 2) *reinterpret_cast<uint32_t*>(dst + e) = pack2<BF16>(acc[e] * inv, acc[e + 1] * inv);
+    if (lane == 0) lse[((int64_t)b * heads + h) * seqlen_q + pos] = wsum > 0.f ? mx + __logf(wsum) : kNegSentinel;
 }
 
 }  // namespace fa
