@@ -197,6 +197,51 @@ int64_t decode_workspace_bytes(const fa_b200_params_t* p) {
     return ((rows * p->head_dim * 4 + 255) & ~(int64_t)255) + ((rows * 4 + 255) & ~(int64_t)255);
 }
 
+// Scheduler state for the persistent kernel: one pair of ints (next work id, CTAs done) per launch.
+// A ring of 1024 pairs per device is allocated (8 KB, zeroed) the first time a device is used -- the only
+// allocation this library ever makes; each launch takes the next pair and the kernel re-zeroes it on exit,
+// so launches on concurrent streams never share a pair unless > 1024 of them are in flight at once.
+int* next_sched_slot(int device) {
+    static int* base[64];
+    static std::once_flag once[64];
+    static std::atomic<unsigned> counter[64];
+    std::call_once(once[device & 63], [&] {
+        int* ptr = nullptr;
+        if (cudaMalloc(&ptr, 1024 * 2 * sizeof(int)) == cudaSuccess && cudaMemset(ptr, 0, 1024 * 2 * sizeof(int)) == cudaSuccess)
+            base[device & 63] = ptr;
+    });
+    int* b = base[device & 63];
+    if (!b) return nullptr;
+    return b + 2 * (counter[device & 63].fetch_add(1, std::memory_order_relaxed) % 1024u);
+}
+
+int sm_count(int device) {
+    static int cached[64];
+    if (cached[device & 63] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+        cached[device & 63] = n;
+    }
+    return cached[device & 63];
+}
+
+// Persistent 1-D grid; work items in sectioned longest-first order (see FwdKernelParams::section_bh).
+dim3 set_launch_order(fa::FwdKernelParams& kp, int device, int batch, int heads, int heads_k, int max_seqlen_q, int max_seqlen_k, int head_dim) {
+    kp.num_m_blocks = (max_seqlen_q + 255) / 256;
+    kp.num_bh = batch * heads;
+    // K+V bytes one kv head streams; keep a section's K/V within ~32 MB of the 126 MB L2
+    const int64_t kv_bytes = 2ll * max_seqlen_k * head_dim * 2;
+    const int group = heads / heads_k;
+    int64_t sec = (32ll << 20) / (kv_bytes > 0 ? kv_bytes : 1) * group;
+    if (sec < group) sec = group;
+    if (sec > kp.num_bh) sec = kp.num_bh;
+    kp.section_bh = (int)sec;
+    kp.sched = next_sched_slot(device);
+    const int64_t total = (int64_t)kp.num_m_blocks * kp.num_bh;
+    const int sms = sm_count(device);
+    return dim3((unsigned)(total < sms ? total : sms), 1, 1);
+}
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -295,7 +340,8 @@ FA_B200_API int fa_b200_fwd(const fa_b200_params_t* p, void* stream_v) {
     if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, p->seqlen_k, p->batch, p->v_stride_h, p->v_stride_s, p->v_stride_b, "v")) return rc;
 
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
-    dim3 grid((p->seqlen_q + 255) / 256, p->num_heads, p->batch);
+    dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
+    if (!kp.sched) return fail(FA_B200_EINVAL, "could not allocate the 8 KB tile-scheduler buffer on device %d", p->device);
     return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
 }
 
@@ -346,7 +392,8 @@ FA_B200_API int fa_b200_varlen_fwd(const fa_b200_params_t* p, void* stream_v) {
         if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, p->total_k, 1, p->v_stride_h, p->v_stride_s, 0, "v")) return rc;
     }
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
-    dim3 grid((p->seqlen_q + 255) / 256, p->num_heads, p->batch);
+    dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
+    if (!kp.sched) return fail(FA_B200_EINVAL, "could not allocate the 8 KB tile-scheduler buffer on device %d", p->device);
     return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
 }
 
@@ -505,7 +552,8 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
         return 0;
     }
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
-    dim3 grid((p->seqlen_q + 255) / 256, p->num_heads, p->batch);
+    dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
+    if (!kp.sched) return fail(FA_B200_EINVAL, "could not allocate the 8 KB tile-scheduler buffer on device %d", p->device);
     return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
 }
 

@@ -62,11 +62,20 @@ struct alignas(64) FwdKernelParams {
     int window_left;   // -1 = unbounded
     int window_right;  // -1 = unbounded; causal is window_right = 0
     int reverse_m;     // launch the longest query blocks first (causal / local)
+    // 1-D launch order (non-decode): CTAs are numbered section by section; a section is `section_bh`
+    // (batch, head) pairs whose K/V fit L2 together, and inside a section all pairs' longest query block
+    // come first (longest-processing-time-first across the section, not just inside one head).
+    int num_m_blocks;
+    int num_bh;
+    int section_bh;
     // decode mode (packed GQA + split-KV): the 128 tile rows are (query position, head-in-group) pairs
     int gqa_pack;        // query heads per KV head packed into the row dimension
     int num_splits;      // CTAs along the KV length per (batch, kv head); > 1 => partial results
     float* o_partial;    // [split][batch][head][seqlen_q][D] fp32, normalised per split
     float* lse_partial;  // [split][batch][head][seqlen_q] fp32, -inf for an empty split
+    // persistent tile scheduler (non-decode): sched[0] = next work item to hand out, sched[1] = CTAs done;
+    // both are 0 before the launch and reset to 0 by the last CTA to finish.
+    int* sched;
 };
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -94,13 +103,14 @@ struct FwdConfig {
     static constexpr int kKvStages = (D == 128) ? 4 : 6;
     static constexpr int kSmemQ = 2 * kTileBytes;
     static constexpr int kSmemKV = kKvStages * kTileBytes;
-    static constexpr int kNumBars = 2 + 2 * kKvStages + 2 + 2 + 2 + 2 + 2 + 2;
+    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4;
     static constexpr int kOffBars = kSmemQ + kSmemKV;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
     static constexpr int kOffScale = (kOffTmemPtr + 16 + 15) & ~15;
-    static constexpr int kOffRowSum = kOffScale + 2 * 128 * 4;
-    static constexpr int kOffRowMax = kOffRowSum + 2 * 128 * 4;
-    static constexpr int kSmemUsed = kOffRowMax + 2 * 128 * 4;
+    static constexpr int kOffRowSum = kOffScale + 2 * 128 * 4;      // [item parity][stage][128]
+    static constexpr int kOffRowMax = kOffRowSum + 2 * 2 * 128 * 4;  // [item parity][stage][128]
+    static constexpr int kOffSched = kOffRowMax + 2 * 2 * 128 * 4;   // int[2] work ids
+    static constexpr int kSmemUsed = kOffSched + 16;
     static constexpr int kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
     static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
     static constexpr int kTmemPOff = 64;
@@ -143,10 +153,104 @@ FA_DEVICE SeqGeom load_geom(const FwdKernelParams& p, int batch) {
     return g;
 }
 
-// DECODE = false: grid (query blocks of 256 rows, query heads, batch); two query tiles per CTA.
-// DECODE = true : grid (KV splits, KV heads, batch); ONE tile whose 128 rows are the (position, head)
-//                 pairs of a whole GQA group (row = position * G + head_in_group), so a decode step reads
-//                 each K/V byte once per group; only stage 0 runs. HBM-bound by construction.
+// Geometry of one work item (a 256-row query block of one (batch, head); in DECODE mode one KV split
+// of one (batch, kv head) GQA group). Every warp role recomputes it from the work id.
+struct WorkGeom {
+    SeqGeom g;
+    int head, batch, kv_head, split;
+    int m0, m_end;       // query positions [m0, m_end)
+    int off;             // seqlen_k - seqlen_q (bottom-right alignment)
+    int n_min, n_max;    // KV tiles [n_min, n_max)
+    int n_tiles;
+    int it_lo[2], it_hi[2];  // iterations each stage takes part in (iteration it = tile n_max-1-it)
+    int o_b;
+    bool skip;           // nothing to do and nothing to write (query block past the sequence end)
+};
+
+template <bool DECODE>
+FA_DEVICE WorkGeom work_geom(const FwdKernelParams& p, int work_id) {
+    constexpr int BM = 128, BN = 128;
+    WorkGeom w;
+    const int G = DECODE ? p.gqa_pack : 1;
+    int m_block = 0;
+    w.split = 0;
+    if constexpr (DECODE) {
+        w.split = (int)blockIdx.x;
+        w.head = (int)blockIdx.y * G;  // first query head of the group
+        w.batch = blockIdx.z;
+        w.kv_head = blockIdx.y;
+    } else {
+        // sectioned longest-first order, see FwdKernelParams::section_bh
+        const int per_section = p.section_bh * p.num_m_blocks;
+        const int sec = work_id / per_section;
+        const int r = work_id - sec * per_section;
+        const int sec_n = min(p.section_bh, p.num_bh - sec * p.section_bh);
+        const int m_rank = r / sec_n;
+        const int bh = sec * p.section_bh + (r - m_rank * sec_n);
+        m_block = p.reverse_m ? p.num_m_blocks - 1 - m_rank : m_rank;
+        w.head = bh % p.num_heads;
+        w.batch = bh / p.num_heads;
+        w.kv_head = w.head / p.heads_per_kv;
+    }
+    w.g = load_geom(p, w.batch);
+    w.m0 = m_block * (2 * BM);
+    w.skip = w.m0 >= w.g.seqlen_q;  // over-provisioned varlen grid
+    w.m_end = DECODE ? w.g.seqlen_q : min(w.m0 + 2 * BM, w.g.seqlen_q);
+    w.off = w.g.seqlen_k - w.g.seqlen_q;
+    w.o_b = p.cu_seqlens_q ? 0 : w.batch;
+    int n_max = (w.g.seqlen_k + BN - 1) / BN;
+    if (p.window_right >= 0) {
+        const int max_col = w.m_end - 1 + w.off + p.window_right;
+        n_max = min(n_max, max_col < 0 ? 0 : max_col / BN + 1);
+    }
+    int n_min = 0;
+    if (p.window_left >= 0) {
+        const int min_col = w.m0 + w.off - p.window_left;
+        n_min = max(0, min_col >= 0 ? min_col / BN : 0);
+    }
+    if constexpr (DECODE) {  // this CTA's share of the KV tiles
+        const int per = (max(n_max - n_min, 0) + p.num_splits - 1) / p.num_splits;
+        const int lo = n_min + w.split * per;
+        n_max = min(n_max, lo + per);
+        n_min = min(lo, n_max);
+    }
+    w.n_min = n_min;
+    w.n_max = n_max;
+    w.n_tiles = w.skip ? 0 : max(n_max - n_min, 0);
+    // Stage s (rows m0+128s ..) only takes part in iterations [it_lo[s], it_hi[s]): tiles wholly above its
+    // causal diagonal or wholly left of its window are skipped for that stage.
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int r0 = w.m0 + s * BM;
+        int hi_n = n_max, lo_n = n_min;
+        if (DECODE) {
+            if (s == 1) hi_n = lo_n = n_min;  // single tile of packed rows: stage 1 is idle
+        } else if (r0 >= w.g.seqlen_q) {
+            hi_n = lo_n = n_min;  // no valid row in this stage
+        } else {
+            if (p.window_right >= 0) {
+                const int max_col = min(r0 + BM, w.g.seqlen_q) - 1 + w.off + p.window_right;
+                hi_n = min(n_max, max_col < 0 ? 0 : max_col / BN + 1);
+            }
+            if (p.window_left >= 0) {
+                const int min_col = r0 + w.off - p.window_left;
+                lo_n = max(n_min, min_col >= 0 ? min_col / BN : 0);
+            }
+            hi_n = max(hi_n, lo_n);
+        }
+        w.it_lo[s] = n_max - hi_n;
+        w.it_hi[s] = n_max - lo_n;
+        if (w.n_tiles == 0) w.it_lo[s] = w.it_hi[s] = 0;
+    }
+    return w;
+}
+
+// DECODE = false: persistent grid (one CTA per SM); work items = (256-row query block, head, batch) handed
+//                 out longest-first by an atomic counter, so the prologue of the next item (Q/K loads, first
+//                 QK^T) overlaps the epilogue of the current one and TMEM / barriers are set up once.
+// DECODE = true : grid (KV splits, KV heads, batch), one item per CTA; ONE tile whose 128 rows are the
+//                 (position, head) pairs of a whole GQA group (row = position * G + head_in_group), so a
+//                 decode step reads each K/V byte once per group; only stage 0 runs. HBM-bound by construction.
 template <int D, bool BF16, bool FEAT, bool DECODE = false>
 __global__ void __launch_bounds__(512, 1)
 fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
@@ -161,91 +265,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
     const int G = DECODE ? p.gqa_pack : 1;
-    const int m_block = DECODE ? 0 : (p.reverse_m ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x);
-    const int split = DECODE ? (int)blockIdx.x : 0;
-    const int head = DECODE ? (int)blockIdx.y * G : (int)blockIdx.y;  // first query head of the group
-    const int batch = blockIdx.z;
-    const SeqGeom g = load_geom(p, batch);
-    const int m0 = m_block * (2 * BM);
-    if (m0 >= g.seqlen_q) return;  // over-provisioned varlen grid
-    // query positions covered by this CTA: [m0, m_end)
-    const int m_end = DECODE ? g.seqlen_q : min(m0 + 2 * BM, g.seqlen_q);
-
-    // KV tile range [n_min, n_max) visible to these query rows (bottom-right aligned).
-    const int off = g.seqlen_k - g.seqlen_q;
-    int n_max = (g.seqlen_k + BN - 1) / BN;
-    if (p.window_right >= 0) {
-        const int max_col = m_end - 1 + off + p.window_right;
-        n_max = min(n_max, max_col < 0 ? 0 : max_col / BN + 1);
-    }
-    int n_min = 0;
-    if (p.window_left >= 0) {
-        const int min_col = m0 + off - p.window_left;
-        n_min = max(0, min_col >= 0 ? min_col / BN : 0);
-    }
-    if constexpr (DECODE) {  // this CTA's share of the KV tiles
-        const int per = (max(n_max - n_min, 0) + p.num_splits - 1) / p.num_splits;
-        const int lo = n_min + split * per;
-        n_max = min(n_max, lo + per);
-        n_min = min(lo, n_max);
-    }
-    const int n_tiles = n_max - n_min;
-    const int o_b = p.cu_seqlens_q ? 0 : batch;
+    const int total_work = DECODE ? 1 : p.num_m_blocks * p.num_bh;
+    const int num_batch = DECODE ? (int)gridDim.z : p.num_bh / p.num_heads;
     const bool partial_out = DECODE && p.num_splits > 1;
-
-    if (n_tiles <= 0) {
-        // No visible key for any row of this block: out = 0, lse = sentinel
-        // (reference kernel/fused_mha_forward_varlen.cu:100-111). A decode split with no tile writes an
-        // ignorable partial (lse = -inf).
-        const int rows = (m_end - m0) * G;  // packed rows: position-major, head-in-group minor
-        if (partial_out) {
-            for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-                const int pos = r / G, h = head + r % G;
-                p.lse_partial[(((int64_t)split * gridDim.z + batch) * p.num_heads + h) * g.seqlen_q + pos] = -INFINITY;
-            }
-            return;
-        }
-        uint16_t* outp = reinterpret_cast<uint16_t*>(p.out);
-        for (int idx = threadIdx.x; idx < rows * (D / 8); idx += blockDim.x) {
-            const int r = idx / (D / 8), c = idx % (D / 8);
-            const int pos = m0 + r / G, h = head + r % G;
-            uint16_t* dst = outp + o_b * p.o_stride_b + (int64_t)(g.q_off + pos) * p.o_stride_s + h * p.o_stride_h + c * 8;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-        }
-        for (int r = threadIdx.x; r < rows; r += blockDim.x)
-            p.lse[o_b * p.lse_stride_b + (head + r % G) * p.lse_stride_h + g.q_off + m0 + r / G] = kNegSentinel;
-        return;
-    }
-
-    // Iterations run over KV tiles in DESCENDING order: iteration `it` handles tile n_max-1-it, so the
-    // masked (diagonal / ragged-tail) tiles come first. Stage s (rows m0+128s ..) only takes part in
-    // iterations [it_lo[s], it_hi[s]): tiles wholly above its causal diagonal or wholly left of its
-    // window are skipped for that stage (the K/V tile is still streamed for the other stage).
-    int it_lo[2], it_hi[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const int r0 = m0 + s * BM;
-        int hi_n = n_max, lo_n = n_min;
-        if (DECODE) {
-            if (s == 1) hi_n = lo_n = n_min;  // single tile of packed rows: stage 1 is idle
-        } else if (r0 >= g.seqlen_q) {
-            hi_n = lo_n = n_min;  // no valid row in this stage
-        } else {
-            if (p.window_right >= 0) {
-                const int max_col = min(r0 + BM, g.seqlen_q) - 1 + off + p.window_right;
-                hi_n = min(n_max, max_col < 0 ? 0 : max_col / BN + 1);
-            }
-            if (p.window_left >= 0) {
-                const int min_col = r0 + off - p.window_left;
-                lo_n = max(n_min, min_col >= 0 ? min_col / BN : 0);
-            }
-            hi_n = max(hi_n, lo_n);
-        }
-        it_lo[s] = n_max - hi_n;
-        it_hi[s] = n_max - lo_n;
-    }
 
     // ------------------------------------------------------------------ shared-memory carve-up
     const uint32_t sQ = sbase;
@@ -254,16 +277,22 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     auto bar_q_full = [&](int s) { return bars + 8 * s; };
     auto bar_kv_full = [&](int i) { return bars + 8 * (2 + i); };
     auto bar_kv_empty = [&](int i) { return bars + 8 * (2 + KV + i); };
-    auto bar_s_full = [&](int s) { return bars + 8 * (2 + 2 * KV + s); };   // MMA -> softmax: S_s ready
-    auto bar_p_full = [&](int s) { return bars + 8 * (4 + 2 * KV + s); };   // softmax+correction -> MMA
-    auto bar_stats = [&](int s) { return bars + 8 * (6 + 2 * KV + s); };    // softmax -> correction: scale
-    auto bar_final = [&](int s) { return bars + 8 * (8 + 2 * KV + s); };    // softmax -> correction: l, m
-    auto bar_o_full = [&](int s) { return bars + 8 * (10 + 2 * KV + s); };  // MMA -> correction: O_s final
-    auto bar_p_last = [&](int s) { return bars + 8 * (12 + 2 * KV + s); };  // softmax -> MMA: last 1/4 of P
+    constexpr int kB0 = 2 + 2 * KV;
+    auto bar_s_full = [&](int s) { return bars + 8 * (kB0 + s); };       // MMA -> softmax: S_s ready
+    auto bar_p_full = [&](int s) { return bars + 8 * (kB0 + 2 + s); };   // softmax+correction -> MMA
+    auto bar_stats = [&](int s) { return bars + 8 * (kB0 + 4 + s); };    // softmax -> correction: scale
+    auto bar_o_full = [&](int s) { return bars + 8 * (kB0 + 6 + s); };   // MMA -> correction: O_s final
+    auto bar_p_last = [&](int s) { return bars + 8 * (kB0 + 8 + s); };   // softmax -> MMA: last 1/4 of P
+    auto bar_final = [&](int s, int b) { return bars + 8 * (kB0 + 10 + 2 * s + b); };  // softmax -> corr.: l, m
+    const uint32_t bar_q_empty = bars + 8 * (kB0 + 14);                  // MMA -> loader: Q tiles consumed
+    auto bar_sched_full = [&](int b) { return bars + 8 * (kB0 + 15 + b); };   // loader -> everyone: work id
+    auto bar_sched_empty = [&](int b) { return bars + 8 * (kB0 + 17 + b); };  // everyone -> loader
+    static_assert(kB0 + 19 <= Cfg::kNumBars, "barrier table too small");
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffTmemPtr);
     float* sScale = reinterpret_cast<float*>(sgen + Cfg::kOffScale);
     float* sRowSum = reinterpret_cast<float*>(sgen + Cfg::kOffRowSum);
     float* sRowMax = reinterpret_cast<float*>(sgen + Cfg::kOffRowMax);
+    volatile int* sSched = reinterpret_cast<volatile int*>(sgen + Cfg::kOffSched);
 
     if (warp == 13 && lane == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -271,10 +300,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             mbar_init(bar_s_full(s), 1);
             mbar_init(bar_p_full(s), 8);  // 4 softmax warps + 4 correction warps
             mbar_init(bar_stats(s), 4);
-            mbar_init(bar_final(s), 4);
             mbar_init(bar_o_full(s), 1);
             mbar_init(bar_p_last(s), 4);
+            mbar_init(bar_final(s, 0), 4);
+            mbar_init(bar_final(s, 1), 4);
+            mbar_init(bar_sched_full(s), 1);
+            mbar_init(bar_sched_empty(s), 13);  // MMA warp + 8 softmax warps + 4 correction warps
         }
+        mbar_init(bar_q_empty, 1);
         for (int i = 0; i < KV; ++i) {
             mbar_init(bar_kv_full(i), 1);
             mbar_init(bar_kv_empty(i), 1);
@@ -290,10 +323,21 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int kv_head = DECODE ? (int)blockIdx.y : head / p.heads_per_kv;
+    // Consumer side of the scheduler: k-th work id of this CTA (>= total_work means "no more work").
+    auto get_work = [&](int k) -> int {
+        if constexpr (DECODE) {
+            return k == 0 ? 0 : total_work;
+        } else {
+            mbar_wait(bar_sched_full(k & 1), (k >> 1) & 1);
+            const int id = sSched[k & 1];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sched_empty(k & 1));
+            return id;
+        }
+    };
 
     if (warp == 13) {
-        // ============================================================ TMA producer
+        // ============================================================ TMA producer + tile scheduler
         reg_dec<48>();
         auto load_tile = [&](const CUtensorMap* tm, uint32_t dst, uint32_t bar, int h, int row, int b) {
             mbar_arrive_expect_tx(bar, Cfg::kTileBytes);
@@ -301,38 +345,76 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             for (int c = 0; c < D / 64; ++c)
                 tma_load_4d(dst + c * Cfg::kHalfBytes, tm, bar, c * 64, h, row, b);
         };
-        auto kv_coords = [&](int n, int& row, int& b) {
-            const int r = n * BN;
-            if (p.block_table) {
-                const int page = r / p.page_size;
-                b = p.block_table[(int64_t)batch * p.block_table_stride + page];
-                row = r - page * p.page_size;
-            } else {
-                b = g.k_b;
-                row = g.k_off + r;
+        int ring = 0;  // K of iteration it is ring entry (base + 2*it), V is (base + 2*it + 1)
+        int ka = 0;    // items with work so far
+        int id = DECODE ? 0 : (int)blockIdx.x;
+        for (int k = 0;; ++k) {
+            if constexpr (!DECODE) {
+                // publish the k-th work id (slot k&1 is free once everyone consumed item k-2)
+                if (k >= 2) mbar_wait(bar_sched_empty(k & 1), ((k >> 1) - 1) & 1);
+                if (lane == 0) {
+                    sSched[k & 1] = id;
+                    mbar_arrive(bar_sched_full(k & 1));
+                }
+                __syncwarp();
+            } else if (k > 0) {
+                id = total_work;
             }
-        };
-        int ring = 0;  // K of iteration it is ring entry 2*it, V is 2*it+1
-        auto produce = [&](const CUtensorMap* tm, int n) {
-            const int slot = ring % KV;
-            const uint32_t parity = ((ring / KV) & 1) ^ 1;
-            mbar_wait(bar_kv_empty(slot), parity);
+            if (id >= total_work) break;
+            const WorkGeom w = work_geom<DECODE>(p, id);
+            int next_id = total_work;
+            if constexpr (!DECODE) {  // fetch the next item early: the atomic's latency hides behind the loads
+                if (lane == 0) next_id = atomicAdd(p.sched, 1) + (int)gridDim.x;
+                next_id = __shfl_sync(0xffffffffu, next_id, 0);
+            }
+            if (w.n_tiles > 0) {
+                auto kv_coords = [&](int n, int& row, int& b) {
+                    const int r = n * BN;
+                    if (p.block_table) {
+                        const int page = r / p.page_size;
+                        b = p.block_table[(int64_t)w.batch * p.block_table_stride + page];
+                        row = r - page * p.page_size;
+                    } else {
+                        b = w.g.k_b;
+                        row = w.g.k_off + r;
+                    }
+                };
+                auto produce = [&](const CUtensorMap* tm, int n) {
+                    const int slot = ring % KV;
+                    const uint32_t parity = ((ring / KV) & 1) ^ 1;
+                    mbar_wait(bar_kv_empty(slot), parity);
+                    if (lane == 0) {
+                        int row, b;
+                        kv_coords(n, row, b);
+                        load_tile(tm, sKV + slot * Cfg::kTileBytes, bar_kv_full(slot), w.kv_head, row, b);
+                    }
+                    ++ring;
+                };
+                // Q tiles of the previous item must have been consumed by its last QK^T
+                mbar_wait(bar_q_empty, (ka & 1) ^ 1);
+                // DECODE: tm_q's box is (64, G, 128/G, 1), so one load brings the G heads of 128/G positions
+                if (lane == 0) load_tile(&p.tm_q, sQ, bar_q_full(0), w.head, w.g.q_off + w.m0, w.g.q_b);
+                produce(&p.tm_k, w.n_max - 1);
+                if (!DECODE && lane == 0)
+                    load_tile(&p.tm_q, sQ + Cfg::kTileBytes, bar_q_full(1), w.head, w.g.q_off + w.m0 + BM, w.g.q_b);
+                produce(&p.tm_v, w.n_max - 1);
+                for (int it = 1; it < w.n_tiles; ++it) {
+                    produce(&p.tm_k, w.n_max - 1 - it);
+                    produce(&p.tm_v, w.n_max - 1 - it);
+                }
+                ++ka;
+            }
+            id = next_id;
+        }
+        if constexpr (!DECODE) {
+            // the last CTA to run out of work re-arms the scheduler for the next launch
             if (lane == 0) {
-                int row, b;
-                kv_coords(n, row, b);
-                load_tile(tm, sKV + slot * Cfg::kTileBytes, bar_kv_full(slot), kv_head, row, b);
+                const int done = atomicAdd(p.sched + 1, 1);
+                if (done == (int)gridDim.x - 1) {
+                    p.sched[0] = 0;
+                    p.sched[1] = 0;
+                }
             }
-            ++ring;
-        };
-        // DECODE: tm_q's box is (64, G, 128/G, 1), so one load brings the G heads of 128/G positions
-        if (lane == 0) load_tile(&p.tm_q, sQ, bar_q_full(0), head, g.q_off + m0, g.q_b);
-        produce(&p.tm_k, n_max - 1);
-        if (!DECODE && lane == 0)
-            load_tile(&p.tm_q, sQ + Cfg::kTileBytes, bar_q_full(1), head, g.q_off + m0 + BM, g.q_b);
-        produce(&p.tm_v, n_max - 1);
-        for (int it = 1; it < n_tiles; ++it) {
-            produce(&p.tm_k, n_max - 1 - it);
-            produce(&p.tm_v, n_max - 1 - it);
         }
     } else if (warp == 12) {
         // ============================================================ MMA issuer
@@ -341,7 +423,6 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         constexpr uint32_t idesc_pv = umma_idesc_f16(BF16, BM, D, false, true);
         const uint32_t tS[2] = {tmem_base + Cfg::kTmemS0, tmem_base + Cfg::kTmemS1};
         const uint32_t tO[2] = {tmem_base + Cfg::kTmemO0, tmem_base + Cfg::kTmemO1};
-
         // Descriptor words (ptx_sm100.cuh): lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version | swizzle.
         // Q, K: K-major, 128B swizzle, 8-row groups 1024 B apart (LBO unused = 1).
         // V: MN-major B operand: 64-column blocks kHalfBytes apart (LBO), 8-row groups 1024 B apart (SBO).
@@ -359,41 +440,59 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         auto slot_addr = [&](int r) { return sKV + (r % KV) * Cfg::kTileBytes; };
         auto wait_full = [&](int r) { mbar_wait(bar_kv_full(r % KV), (r / KV) & 1); };
 
-        mbar_wait(bar_q_full(0), 0);
-        // Issue order per iteration: PV0(it-1) QK0(it) PV1(it-1) QK1(it). tcgen05 ops execute in issue
-        // order, so S_s(it) may overwrite the columns P_s(it-1) lives in without a barrier.
-        for (int it = 0; it <= n_tiles; ++it) {
-            if (it > 0) wait_full(2 * it - 1);
-            if (it < n_tiles) wait_full(2 * it);
-            if (!DECODE && it == 0) mbar_wait(bar_q_full(1), 0);
+        int ring = 0;           // ring entries consumed by earlier items
+        int ka = 0;             // items with work so far
+        int steps[2] = {0, 0};  // softmax steps of earlier items, per stage (barrier phase bookkeeping)
+        for (int k = 0;; ++k) {
+            const int id = get_work(k);
+            if (id >= total_work) break;
+            const WorkGeom w = work_geom<DECODE>(p, id);
+            if (w.n_tiles <= 0) continue;
+            mbar_wait(bar_q_full(0), ka & 1);
+            // Issue order per iteration: PV0(it-1) QK0(it) PV1(it-1) QK1(it). tcgen05 ops execute in issue
+            // order, so S_s(it) may overwrite the columns P_s(it-1) lives in without a barrier, and the
+            // first QK^T of the next item may follow the last P V of this one directly.
+            for (int it = 0; it <= w.n_tiles; ++it) {
+                if (it > 0) wait_full(ring + 2 * it - 1);
+                if (it < w.n_tiles) wait_full(ring + 2 * it);
+                if (!DECODE && it == 0) mbar_wait(bar_q_full(1), ka & 1);
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const bool do_pv = it > 0 && (it - 1) >= it_lo[s] && (it - 1) < it_hi[s];
-                const bool do_qk = it < n_tiles && it >= it_lo[s] && it < it_hi[s];
-                if (do_pv) {
-                    const int j = it - 1 - it_lo[s];
-                    const uint32_t tP = tS[s] + Cfg::kTmemPOff;
-                    const uint32_t v_lo = lo_addr(slot_addr(2 * it - 1)) | kLoVmn;
-                    mbar_wait(bar_p_full(s), j & 1);
-                    tc_fence_after();
-                    if (FA_SPLIT_P) {
-                        umma_issue_pv_k0_6(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, j > 0 ? 1u : 0u);
-                        mbar_wait(bar_p_last(s), j & 1);
+                for (int s = 0; s < 2; ++s) {
+                    const bool do_pv = it > 0 && (it - 1) >= w.it_lo[s] && (it - 1) < w.it_hi[s];
+                    const bool do_qk = it < w.n_tiles && it >= w.it_lo[s] && it < w.it_hi[s];
+                    if (do_pv) {
+                        const int j = it - 1 - w.it_lo[s];
+                        const uint32_t ph = (steps[s] + j) & 1;
+                        const uint32_t tP = tS[s] + Cfg::kTmemPOff;
+                        const uint32_t v_lo = lo_addr(slot_addr(ring + 2 * it - 1)) | kLoVmn;
+                        // P_s(j) written, O_s rescaled; for j == 0 this also means the correction warps
+                        // finished reading O_s of the previous item (their arrival comes after that epilogue)
+                        mbar_wait(bar_p_full(s), ph);
                         tc_fence_after();
-                        umma_issue_pv_k6_8(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, 1u);
-                    } else {
-                        umma_issue_pv_k0_8(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, j > 0 ? 1u : 0u);
+                        if (FA_SPLIT_P) {
+                            umma_issue_pv_k0_6(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, j > 0 ? 1u : 0u);
+                            mbar_wait(bar_p_last(s), ph);
+                            tc_fence_after();
+                            umma_issue_pv_k6_8(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, 1u);
+                        } else {
+                            umma_issue_pv_k0_8(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, j > 0 ? 1u : 0u);
+                        }
+                        if (it == w.it_hi[s]) umma_commit_elect(bar_o_full(s));
                     }
-                    if (it == it_hi[s]) umma_commit_elect(bar_o_full(s));
+                    if (do_qk) {
+                        tc_fence_after();
+                        issue_qk(s, slot_addr(ring + 2 * it));
+                        umma_commit_elect(bar_s_full(s));
+                    }
                 }
-                if (do_qk) {
-                    tc_fence_after();
-                    issue_qk(s, slot_addr(2 * it));
-                    umma_commit_elect(bar_s_full(s));
-                }
+                if (it > 0) umma_commit_elect(bar_kv_empty((ring + 2 * it - 1) % KV));
+                if (it < w.n_tiles) umma_commit_elect(bar_kv_empty((ring + 2 * it) % KV));
+                if (it == w.n_tiles - 1) umma_commit_elect(bar_q_empty);  // last QK^T of the item issued
             }
-            if (it > 0) umma_commit_elect(bar_kv_empty((2 * it - 1) % KV));
-            if (it < n_tiles) umma_commit_elect(bar_kv_empty((2 * it) % KV));
+            ring += 2 * w.n_tiles;
+            steps[0] += w.it_hi[0] - w.it_lo[0];
+            steps[1] += w.it_hi[1] - w.it_lo[1];
+            ++ka;
         }
     } else if (warp < 8) {
         // ============================================================ softmax (stage = warp / 4)
@@ -403,206 +502,253 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tmem_base + lane_off + (s == 0 ? Cfg::kTmemS0 : Cfg::kTmemS1);
         const uint32_t tP = tS + Cfg::kTmemPOff;
-        const int i_glob = DECODE ? row / G : m0 + s * BM + row;  // query position inside the sequence
-        const int my_lo = s == 0 ? it_lo[0] : it_lo[1];
-        const int my_n = (s == 0 ? it_hi[0] : it_hi[1]) - my_lo;
-
-        // visible key range of this row: [col_lo, col_hi)
-        int col_hi = g.seqlen_k;
-        if (p.window_right >= 0) col_hi = min(col_hi, i_glob + off + p.window_right + 1);
-        int col_lo = 0;
-        if (p.window_left >= 0) col_lo = max(0, i_glob + off - p.window_left);
-        const unsigned col_width = (unsigned)max(col_hi - col_lo, 0);
-
         const float sl2 = FEAT ? 1.0f : p.scale_log2;
-        float slope = 0.f, inv_cap = 0.f;
-        if constexpr (FEAT) {
-            if (p.alibi) slope = p.alibi[batch * p.alibi_stride_b + head + (DECODE ? row % G : 0)];
-            if (p.softcap > 0.f) inv_cap = 1.0f / p.softcap;
-        }
+        int steps = 0;  // softmax steps of earlier items (barrier phase bookkeeping)
+        int items = 0;  // earlier items in which this stage took part
 
-        float m_ref = -INFINITY;  // running reference max (raw score units; log2 units if FEAT)
-        float row_sum = 0.f;
+        for (int k = 0;; ++k) {
+            const int id = get_work(k);
+            if (id >= total_work) break;
+            const WorkGeom w = work_geom<DECODE>(p, id);
+            const int my_lo = s == 0 ? w.it_lo[0] : w.it_lo[1];
+            const int my_n = (s == 0 ? w.it_hi[0] : w.it_hi[1]) - my_lo;
+            if (my_n <= 0) continue;
+            const int i_glob = DECODE ? row / G : w.m0 + s * BM + row;  // query position inside the sequence
 
-        for (int j = 0; j < my_n; ++j) {
-            const int j0 = (n_max - 1 - (my_lo + j)) * BN;
-            mbar_wait(bar_s_full(s), j & 1);
-            tc_fence_after();
-            float v[BN];
-            tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
+            // visible key range of this row: [col_lo, col_hi)
+            int col_hi = w.g.seqlen_k;
+            if (p.window_right >= 0) col_hi = min(col_hi, i_glob + w.off + p.window_right + 1);
+            int col_lo = 0;
+            if (p.window_left >= 0) col_lo = max(0, i_glob + w.off - p.window_left);
+            const unsigned col_width = (unsigned)max(col_hi - col_lo, 0);
 
+            float slope = 0.f, inv_cap = 0.f;
             if constexpr (FEAT) {
-                // reference order (include/mat_mul.h:111-117): scale, ALiBi, then softcap
-                const int rel0 = i_glob + off - j0;
-#pragma unroll
-                for (int c = 0; c < BN; ++c) {
-                    float u = v[c] * p.scale;
-                    u -= slope * fabsf((float)(rel0 - c));
-                    if (p.softcap > 0.f) u = p.softcap * tanh_approx(u * inv_cap);
-                    v[c] = u * kLog2e;
-                }
-            }
-            const bool need_mask = (j0 + BN > col_hi) || (j0 < col_lo);
-            if (__any_sync(0xffffffffu, need_mask)) {
-                const int base = j0 - col_lo;
-#pragma unroll
-                for (int c = 0; c < BN; ++c)
-                    v[c] = ((unsigned)(base + c) < col_width) ? v[c] : -INFINITY;
+                if (p.alibi) slope = p.alibi[w.batch * p.alibi_stride_b + w.head + (DECODE ? row % G : 0)];
+                if (p.softcap > 0.f) inv_cap = 1.0f / p.softcap;
             }
 
-            // row max: four independent 3-input max chains
-            float mx[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) mx[a] = fmaxf(v[2 * a], v[2 * a + 1]);
-#pragma unroll
-            for (int c = 8; c < BN; c += 8) {
-#pragma unroll
-                for (int a = 0; a < 4; ++a) mx[a] = fmax3(mx[a], v[c + 2 * a], v[c + 2 * a + 1]);
-            }
-            const float m_new = fmaxf(m_ref, fmax3(fmaxf(mx[0], mx[1]), mx[2], mx[3]));
-            const float m_new_safe = (m_new == -INFINITY) ? 0.f : m_new;
+            float m_ref = -INFINITY;  // running reference max (raw score units; log2 units if FEAT)
+            float row_sum = 0.f;
 
-            float acc_scale = 1.0f;
-            if (j == 0) {
-                m_ref = m_new;
-            } else {
-                const float d = (m_ref - m_new_safe) * sl2;  // <= 0, -inf if nothing was visible yet
-                if (d < -kRescaleThreshold) {
-                    acc_scale = ex2_approx(d);
-                    m_ref = m_new;
-                }
-            }
-            sScale[s * BM + row] = acc_scale;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_stats(s));
+            for (int j = 0; j < my_n; ++j) {
+                const int j0 = (w.n_max - 1 - (my_lo + j)) * BN;
+                mbar_wait(bar_s_full(s), (steps + j) & 1);
+                tc_fence_after();
+                float v[BN];
+                tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
 
-            const float m_used = (m_ref == -INFINITY) ? 0.f : m_ref;
-            const float neg_m = -m_used * sl2;
-            float sum0 = 0.f, sum1 = 0.f;
+                if constexpr (FEAT) {
+                    // reference order (include/mat_mul.h:111-117): scale, ALiBi, then softcap
+                    const int rel0 = i_glob + w.off - j0;
 #pragma unroll
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    float p0 = v[ch * 32 + c], p1 = v[ch * 32 + c + 1];
-                    fma2(p0, p1, sl2, sl2, neg_m, neg_m);
-                    if (FA_EMU_COUNT > 0 && ((c / 2) % FA_EMU_PERIOD) >= FA_EMU_PERIOD - FA_EMU_COUNT) {
-                        ex2_emu2(p0, p1);
-                    } else {
-                        p0 = ex2_approx(p0);
-                        p1 = ex2_approx(p1);
+                    for (int c = 0; c < BN; ++c) {
+                        float u = v[c] * p.scale;
+                        u -= slope * fabsf((float)(rel0 - c));
+                        if (p.softcap > 0.f) u = p.softcap * tanh_approx(u * inv_cap);
+                        v[c] = u * kLog2e;
                     }
-                    add2(sum0, sum1, p0, p1);
-                    pk[c / 2] = pack2<BF16>(p0, p1);
                 }
-                tmem_st_x16(tP + ch * 16, pk);
-                if (FA_SPLIT_P && ch == BN / 32 - 2) {  // 3/4 of P is on its way: let P V start
-                    tmem_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_p_full(s));
+                const bool need_mask = (j0 + BN > col_hi) || (j0 < col_lo);
+                if (__any_sync(0xffffffffu, need_mask)) {
+                    const int base = j0 - col_lo;
+#pragma unroll
+                    for (int c = 0; c < BN; ++c)
+                        v[c] = ((unsigned)(base + c) < col_width) ? v[c] : -INFINITY;
                 }
+
+                // row max: four independent 3-input max chains
+                float mx[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) mx[a] = fmaxf(v[2 * a], v[2 * a + 1]);
+#pragma unroll
+                for (int c = 8; c < BN; c += 8) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) mx[a] = fmax3(mx[a], v[c + 2 * a], v[c + 2 * a + 1]);
+                }
+                const float m_new = fmaxf(m_ref, fmax3(fmaxf(mx[0], mx[1]), mx[2], mx[3]));
+                const float m_new_safe = (m_new == -INFINITY) ? 0.f : m_new;
+
+                float acc_scale = 1.0f;
+                if (j == 0) {
+                    m_ref = m_new;
+                } else {
+                    const float d = (m_ref - m_new_safe) * sl2;  // <= 0, -inf if nothing was visible yet
+                    if (d < -kRescaleThreshold) {
+                        acc_scale = ex2_approx(d);
+                        m_ref = m_new;
+                    }
+                }
+                sScale[s * BM + row] = acc_scale;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_stats(s));
+
+                const float m_used = (m_ref == -INFINITY) ? 0.f : m_ref;
+                const float neg_m = -m_used * sl2;
+                float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int c = 0; c < 32; c += 2) {
+                        float p0 = v[ch * 32 + c], p1 = v[ch * 32 + c + 1];
+                        fma2(p0, p1, sl2, sl2, neg_m, neg_m);
+                        if (FA_EMU_COUNT > 0 && ((c / 2) % FA_EMU_PERIOD) >= FA_EMU_PERIOD - FA_EMU_COUNT) {
+                            ex2_emu2(p0, p1);
+                        } else {
+                            p0 = ex2_approx(p0);
+                            p1 = ex2_approx(p1);
+                        }
+                        add2(sum0, sum1, p0, p1);
+                        pk[c / 2] = pack2<BF16>(p0, p1);
+                    }
+                    tmem_st_x16(tP + ch * 16, pk);
+                    if (FA_SPLIT_P && ch == BN / 32 - 2) {  // 3/4 of P is on its way: let P V start
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_p_full(s));
+                    }
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(FA_SPLIT_P ? bar_p_last(s) : bar_p_full(s));
+                row_sum = row_sum * acc_scale + (sum0 + sum1);
             }
-            tmem_wait_st();
-            tc_fence_before();
+            // final statistics, double-buffered by item parity (the next item's may be ready before the
+            // correction warps have read this one's)
+            const int fb = items & 1;
+            sRowSum[(fb * 2 + s) * BM + row] = row_sum;
+            sRowMax[(fb * 2 + s) * BM + row] = ((m_ref == -INFINITY) ? 0.f : m_ref) * sl2;
             __syncwarp();
-            if (lane == 0) mbar_arrive(FA_SPLIT_P ? bar_p_last(s) : bar_p_full(s));
-            row_sum = row_sum * acc_scale + (sum0 + sum1);
+            if (lane == 0) mbar_arrive(bar_final(s, fb));
+            steps += my_n;
+            ++items;
         }
-        sRowSum[s * BM + row] = row_sum;
-        sRowMax[s * BM + row] = ((m_ref == -INFINITY) ? 0.f : m_ref) * sl2;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_final(s));
     } else if (warp < 12) {
         // ============================================================ correction + epilogue
         reg_dec<80>();
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tO[2] = {tmem_base + lane_off + Cfg::kTmemO0, tmem_base + lane_off + Cfg::kTmemO1};
+        uint16_t* outp = reinterpret_cast<uint16_t*>(p.out);
+        int steps[2] = {0, 0};
+        int items[2] = {0, 0};
 
-        for (int it = 0; it < n_tiles; ++it) {
+        for (int k = 0;; ++k) {
+            const int id = get_work(k);
+            if (id >= total_work) break;
+            const WorkGeom w = work_geom<DECODE>(p, id);
+            if (w.skip) continue;
+            if (w.n_tiles <= 0) {
+                // No visible key for any row of this block: out = 0, lse = sentinel (reference
+                // kernel/fused_mha_forward_varlen.cu:100-111). A decode split with no tile writes an
+                // ignorable partial (lse = -inf).
+                const int rows = (w.m_end - w.m0) * G;  // packed rows: position-major, head-in-group minor
+                const int t = (warp - 8) * 32 + lane;
+                if (partial_out) {
+                    for (int r = t; r < rows; r += 128)
+                        p.lse_partial[(((int64_t)w.split * num_batch + w.batch) * p.num_heads + w.head + r % G) *
+                                          w.g.seqlen_q + r / G] = -INFINITY;
+                    continue;
+                }
+                for (int idx = t; idx < rows * (D / 8); idx += 128) {
+                    const int r = idx / (D / 8), c = idx % (D / 8);
+                    uint16_t* dst = outp + w.o_b * p.o_stride_b + (int64_t)(w.g.q_off + w.m0 + r / G) * p.o_stride_s +
+                                    (w.head + r % G) * p.o_stride_h + c * 8;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                }
+                for (int r = t; r < rows; r += 128)
+                    p.lse[w.o_b * p.lse_stride_b + (w.head + r % G) * p.lse_stride_h + w.g.q_off + w.m0 + r / G] = kNegSentinel;
+                continue;
+            }
+            for (int it = 0; it < w.n_tiles; ++it) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if (it < w.it_lo[s] || it >= w.it_hi[s]) continue;
+                    const int j = it - w.it_lo[s];
+                    mbar_wait(bar_stats(s), (steps[s] + j) & 1);
+                    const float sc = sScale[s * BM + row];
+                    if (j > 0 && __any_sync(0xffffffffu, sc != 1.0f)) {
+                        tc_fence_after();
+#pragma unroll
+                        for (int c = 0; c < D / 32; ++c) {
+                            float o[32];
+                            tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) o[e] *= sc;
+                            tmem_st_x32(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
+                        }
+                        tmem_wait_st();
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_p_full(s));
+                }
+            }
+            // epilogue: out = O / l, lse = m + ln(l)   (reference kernel/fused_mha_forward.cu:215-223)
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                if (it < it_lo[s] || it >= it_hi[s]) continue;
-                const int j = it - it_lo[s];
-                mbar_wait(bar_stats(s), j & 1);
-                const float sc = sScale[s * BM + row];
-                if (j > 0 && __any_sync(0xffffffffu, sc != 1.0f)) {
-                    tc_fence_after();
+                if (DECODE && s == 1) continue;  // packed-row mode has a single tile
+                const int i_glob = DECODE ? row / G : w.m0 + s * BM + row;
+                const int h_row = DECODE ? w.head + row % G : w.head;
+                const bool valid = i_glob < w.g.seqlen_q;
+                uint16_t* dst = outp + w.o_b * p.o_stride_b + (int64_t)(w.g.q_off + i_glob) * p.o_stride_s +
+                                h_row * p.o_stride_h;
+                float* lse_dst = p.lse + w.o_b * p.lse_stride_b + h_row * p.lse_stride_h + w.g.q_off + i_glob;
+                if (w.it_hi[s] <= w.it_lo[s]) {  // this stage saw no KV tile: no key is visible to its rows
+                    if (valid) {
+#pragma unroll
+                        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
+                        *lse_dst = kNegSentinel;
+                    }
+                    continue;
+                }
+                const int fb = items[s] & 1;
+                mbar_wait(bar_final(s, fb), (items[s] >> 1) & 1);
+                const float l = sRowSum[(fb * 2 + s) * BM + row];
+                const float mx = sRowMax[(fb * 2 + s) * BM + row];
+                mbar_wait(bar_o_full(s), items[s] & 1);
+                tc_fence_after();
+                const float inv = l > 0.f ? 1.0f / l : 0.f;
+                if (partial_out) {
+                    // split-KV partial: normalised fp32 O and this split's LSE; fa_combine_kernel merges them
+                    const int64_t prow = (((int64_t)w.split * num_batch + w.batch) * p.num_heads + h_row) * w.g.seqlen_q + i_glob;
 #pragma unroll
                     for (int c = 0; c < D / 32; ++c) {
                         float o[32];
                         tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
+                        if (valid) {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) o[e] *= sc;
-                        tmem_st_x32(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
+                            for (int e = 0; e < 32; e += 4)
+                                *reinterpret_cast<float4*>(p.o_partial + prow * D + c * 32 + e) =
+                                    make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
+                        }
                     }
-                    tmem_wait_st();
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_p_full(s));
-            }
-        }
-        // epilogue: out = O / l, lse = m + ln(l)   (reference kernel/fused_mha_forward.cu:215-223)
-        uint16_t* outp = reinterpret_cast<uint16_t*>(p.out);
+                    if (valid) p.lse_partial[prow] = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : -INFINITY;
+                } else {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            if (DECODE && s == 1) continue;  // packed-row mode has a single tile
-            const int i_glob = DECODE ? row / G : m0 + s * BM + row;
-            const int h_row = DECODE ? head + row % G : head;
-            const bool valid = i_glob < g.seqlen_q;
-            uint16_t* dst = outp + o_b * p.o_stride_b + (int64_t)(g.q_off + i_glob) * p.o_stride_s +
-                            h_row * p.o_stride_h;
-            float* lse_dst = p.lse + o_b * p.lse_stride_b + h_row * p.lse_stride_h + g.q_off + i_glob;
-            if (it_hi[s] <= it_lo[s]) {  // this stage saw no KV tile: no key is visible to its rows
-                if (valid) {
+                    for (int c = 0; c < D / 32; ++c) {
+                        float o[32];
+                        tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
+                        if (valid) {
 #pragma unroll
-                    for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
-                    *lse_dst = kNegSentinel;
-                }
-                continue;
-            }
-            mbar_wait(bar_final(s), 0);
-            const float l = sRowSum[s * BM + row];
-            const float mx = sRowMax[s * BM + row];
-            mbar_wait(bar_o_full(s), 0);
-            tc_fence_after();
-            const float inv = l > 0.f ? 1.0f / l : 0.f;
-            if (partial_out) {
-                // split-KV partial: normalised fp32 O and this split's LSE; fa_combine_kernel merges them
-                const int64_t prow = (((int64_t)split * gridDim.z + batch) * p.num_heads + h_row) * g.seqlen_q + i_glob;
-#pragma unroll
-                for (int c = 0; c < D / 32; ++c) {
-                    float o[32];
-                    tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
-                    if (valid) {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 4)
-                            *reinterpret_cast<float4*>(p.o_partial + prow * D + c * 32 + e) =
-                                make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
+                            for (int e = 0; e < 32; e += 8) {
+                                uint4 wv;
+                                wv.x = pack2<BF16>(o[e] * inv, o[e + 1] * inv);
+                                wv.y = pack2<BF16>(o[e + 2] * inv, o[e + 3] * inv);
+                                wv.z = pack2<BF16>(o[e + 4] * inv, o[e + 5] * inv);
+                                wv.w = pack2<BF16>(o[e + 6] * inv, o[e + 7] * inv);
+                                *reinterpret_cast<uint4*>(dst + c * 32 + e) = wv;
+                            }
+                        }
                     }
+                    if (valid) *lse_dst = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : kNegSentinel;
                 }
-                if (valid) p.lse_partial[prow] = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : -INFINITY;
-                continue;
+                steps[s] += w.it_hi[s] - w.it_lo[s];
+                ++items[s];
             }
-#pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
-                float o[32];
-                tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
-                if (valid) {
-#pragma unroll
-                    for (int e = 0; e < 32; e += 8) {
-                        uint4 w;
-                        w.x = pack2<BF16>(o[e] * inv, o[e + 1] * inv);
-                        w.y = pack2<BF16>(o[e + 2] * inv, o[e + 3] * inv);
-                        w.z = pack2<BF16>(o[e + 4] * inv, o[e + 5] * inv);
-                        w.w = pack2<BF16>(o[e + 6] * inv, o[e + 7] * inv);
-                        *reinterpret_cast<uint4*>(dst + c * 32 + e) = w;
-                    }
-                }
-            }
-            if (valid) *lse_dst = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : kNegSentinel;
         }
     } else {
         reg_dec<48>();  // warps 14, 15: spare

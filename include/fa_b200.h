@@ -15,8 +15,9 @@
  *
  * The reference passes at::Tensor objects and allocates its outputs inside the wrapper; a C ABI
  * cannot, so here every tensor is a raw device pointer plus element strides, and the caller
- * allocates `out`, `lse` and `workspace` (sizes below). Nothing in this library allocates device
- * memory or synchronises the stream: every call only enqueues kernels on `stream`.
+ * allocates `out`, `lse` and `workspace` (sizes below). The library never synchronises the stream and
+ * makes exactly one device allocation per device for its whole lifetime (an 8 KB tile-scheduler ring,
+ * the first time that device is used); every call only enqueues kernels on `stream`.
  *
  * Error convention: 0 = success; <0 = invalid argument (FA_B200_EINVAL ...); >0 = cudaError_t of
  * a failed runtime call / launch. fa_b200_last_error() returns a thread-local message for the last
