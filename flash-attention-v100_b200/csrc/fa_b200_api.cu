@@ -298,6 +298,14 @@ void fill_common(fa::FwdKernelParams& kp, const fa_b200_params_t* p, bool causal
 
 extern "C" {
 
+#ifdef FA_TRACE
+// debug builds only: device buffer of 16 warps x 4096 int64 for the event trace
+__attribute__((visibility("default"))) int fa_b200_debug_set_trace(void* dev_ptr) {
+    long long* p = static_cast<long long*>(dev_ptr);
+    return (int)cudaMemcpyToSymbol(fa::g_fa_trace, &p, sizeof(p));
+}
+#endif
+
 FA_B200_API int fa_b200_abi_version(void) { return FA_B200_ABI_VERSION; }
 FA_B200_API const char* fa_b200_last_error(void) { return g_err; }
 FA_B200_API int64_t fa_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -94,6 +94,25 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; O is rescaled only whe
 #define FA_SPLIT_P 1     // signal the MMA warp after 3/4 of P so P V starts before the last quarter
 #endif
 
+// Optional event trace (build with -DFA_TRACE): lane 0 of every warp of CTA 0 appends (event, clock64)
+// pairs to a global buffer set through fa_b200_debug_set_trace(); tools/trace_timeline.py prints the
+// per-iteration timeline. Compiled out of the product build.
+#ifdef FA_TRACE
+__device__ long long* g_fa_trace = nullptr;
+#define FA_TRACE_DECL int trace_n = 0; long long* trace_buf = (blockIdx.x == 0 && g_fa_trace) ? g_fa_trace + (threadIdx.x >> 5) * 4096 : nullptr
+#define FA_TRACE_EV(ev)                                                   \
+    do {                                                                  \
+        if (trace_buf && (threadIdx.x & 31) == 0 && trace_n < 2040) {     \
+            trace_buf[trace_n * 2] = (ev);                                \
+            trace_buf[trace_n * 2 + 1] = clock64();                       \
+            ++trace_n;                                                    \
+        }                                                                 \
+    } while (0)
+#else
+#define FA_TRACE_DECL
+#define FA_TRACE_EV(ev)
+#endif
+
 template <int D>
 struct FwdConfig {
     static constexpr int kBlockM = 128;
@@ -265,6 +284,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    FA_TRACE_DECL;
     const int G = DECODE ? p.gqa_pack : 1;
     const int total_work = DECODE ? 1 : p.num_m_blocks * p.num_bh;
     const int num_batch = DECODE ? (int)gridDim.z : p.num_bh / p.num_heads;
@@ -469,10 +489,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         // finished reading O_s of the previous item (their arrival comes after that epilogue)
                         mbar_wait(bar_p_full(s), ph);
                         tc_fence_after();
+                        FA_TRACE_EV(100 + s);  // MMA: P_s (3/4) + O rescale observed
                         if (FA_SPLIT_P) {
                             umma_issue_pv_k0_6(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, j > 0 ? 1u : 0u);
                             mbar_wait(bar_p_last(s), ph);
                             tc_fence_after();
+                            FA_TRACE_EV(110 + s);  // MMA: last quarter of P_s observed
                             umma_issue_pv_k6_8(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, 1u);
                         } else {
                             umma_issue_pv_k0_8(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, j > 0 ? 1u : 0u);
@@ -483,6 +505,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         tc_fence_after();
                         issue_qk(s, slot_addr(ring + 2 * it));
                         umma_commit_elect(bar_s_full(s));
+                        FA_TRACE_EV(120 + s);  // MMA: QK_s issued
                     }
                 }
                 if (it > 0) umma_commit_elect(bar_kv_empty((ring + 2 * it - 1) % KV));
@@ -535,8 +558,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 const int j0 = (w.n_max - 1 - (my_lo + j)) * BN;
                 mbar_wait(bar_s_full(s), (steps + j) & 1);
                 tc_fence_after();
+                FA_TRACE_EV(1);  // softmax: S observed
                 float v[BN];
                 tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
+                FA_TRACE_EV(2);  // softmax: S in registers
 
                 if constexpr (FEAT) {
                     // reference order (include/mat_mul.h:111-117): scale, ALiBi, then softcap
@@ -582,6 +607,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 sScale[s * BM + row] = acc_scale;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_stats(s));
+                FA_TRACE_EV(3);  // softmax: row max done, stats published
 
                 const float m_used = (m_ref == -INFINITY) ? 0.f : m_ref;
                 const float neg_m = -m_used * sl2;
@@ -608,12 +634,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_p_full(s));
+                        FA_TRACE_EV(4);  // softmax: 3/4 of P published
                     }
                 }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(FA_SPLIT_P ? bar_p_last(s) : bar_p_full(s));
+                FA_TRACE_EV(5);  // softmax: all of P published
                 row_sum = row_sum * acc_scale + (sum0 + sum1);
             }
             // final statistics, double-buffered by item parity (the next item's may be ready before the
@@ -669,6 +697,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     if (it < w.it_lo[s] || it >= w.it_hi[s]) continue;
                     const int j = it - w.it_lo[s];
                     mbar_wait(bar_stats(s), (steps[s] + j) & 1);
+                    FA_TRACE_EV(200 + s);  // correction: stats observed
                     const float sc = sScale[s * BM + row];
                     if (j > 0 && __any_sync(0xffffffffu, sc != 1.0f)) {
                         tc_fence_after();
@@ -711,6 +740,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 const float mx = sRowMax[(fb * 2 + s) * BM + row];
                 mbar_wait(bar_o_full(s), items[s] & 1);
                 tc_fence_after();
+                FA_TRACE_EV(210 + s);  // correction: final O observed
                 const float inv = l > 0.f ? 1.0f / l : 0.f;
                 if (partial_out) {
                     // split-KV partial: normalised fp32 O and this split's LSE; fa_combine_kernel merges them
@@ -748,6 +778,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 }
                 steps[s] += w.it_hi[s] - w.it_lo[s];
                 ++items[s];
+                FA_TRACE_EV(220 + s);  // correction: epilogue of stage s stored
             }
         }
     } else {
