@@ -93,6 +93,32 @@ FA_DEVICE void tma_load_4d_hint(uint32_t dst, const void* tmap, uint32_t bar, in
         "r"(c3), "l"(policy)
         : "memory");
 }
+// 4-D tiled store smem -> global (bulk async group); OOB parts of the box are clipped by the tensor map.
+FA_DEVICE void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+FA_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+FA_DEVICE void tma_store_wait_read() {  // at most N committed groups still reading their smem source
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// L2 prefetch of a tile (no smem destination): hides the DRAM latency of a load issued later
+FA_DEVICE void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+        ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+FA_DEVICE void named_bar_sync(uint32_t id, uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+FA_DEVICE void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 FA_DEVICE uint64_t l2_policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
