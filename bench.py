@@ -200,6 +200,9 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry only the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group(backend="nccl", device_id=dev)
 
     def barrier():
