@@ -122,7 +122,7 @@ struct FwdConfig {
     static constexpr int kKvStages = (D == 128) ? 4 : 6;
     static constexpr int kSmemQ = 2 * kTileBytes;
     static constexpr int kSmemKV = kKvStages * kTileBytes;
-    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4;
+    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1;
     static constexpr int kOffBars = kSmemQ + kSmemKV;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
     static constexpr int kOffScale = (kOffTmemPtr + 16 + 15) & ~15;
@@ -183,6 +183,7 @@ struct WorkGeom {
     int n_tiles;
     int it_lo[2], it_hi[2];  // iterations each stage takes part in (iteration it = tile n_max-1-it)
     int o_b;
+    bool ragged_tail;    // the first tile processed (n_max-1) extends past seqlen_k: its V rows need zeroing
     bool skip;           // nothing to do and nothing to write (query block past the sequence end)
 };
 
@@ -236,6 +237,7 @@ FA_DEVICE WorkGeom work_geom(const FwdKernelParams& p, int work_id) {
     w.n_min = n_min;
     w.n_max = n_max;
     w.n_tiles = w.skip ? 0 : max(n_max - n_min, 0);
+    w.ragged_tail = w.n_tiles > 0 && n_max * BN > w.g.seqlen_k;
     // Stage s (rows m0+128s ..) only takes part in iterations [it_lo[s], it_hi[s]): tiles wholly above its
     // causal diagonal or wholly left of its window are skipped for that stage.
 #pragma unroll
@@ -307,7 +309,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     const uint32_t bar_q_empty = bars + 8 * (kB0 + 14);                  // MMA -> loader: Q tiles consumed
     auto bar_sched_full = [&](int b) { return bars + 8 * (kB0 + 15 + b); };   // loader -> everyone: work id
     auto bar_sched_empty = [&](int b) { return bars + 8 * (kB0 + 17 + b); };  // everyone -> loader
-    static_assert(kB0 + 19 <= Cfg::kNumBars, "barrier table too small");
+    const uint32_t bar_vfix = bars + 8 * (kB0 + 19);  // sanitiser -> MMA: tail rows of the ragged V tile zeroed
+    static_assert(kB0 + 20 <= Cfg::kNumBars, "barrier table too small");
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffTmemPtr);
     float* sScale = reinterpret_cast<float*>(sgen + Cfg::kOffScale);
     float* sRowSum = reinterpret_cast<float*>(sgen + Cfg::kOffRowSum);
@@ -325,9 +328,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             mbar_init(bar_final(s, 0), 4);
             mbar_init(bar_final(s, 1), 4);
             mbar_init(bar_sched_full(s), 1);
-            mbar_init(bar_sched_empty(s), 13);  // MMA warp + 8 softmax warps + 4 correction warps
+            mbar_init(bar_sched_empty(s), 14);  // MMA warp + 8 softmax + 4 correction warps + V sanitiser
         }
         mbar_init(bar_q_empty, 1);
+        mbar_init(bar_vfix, 1);
         for (int i = 0; i < KV; ++i) {
             mbar_init(bar_kv_full(i), 1);
             mbar_init(bar_kv_empty(i), 1);
@@ -462,6 +466,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
 
         int ring = 0;           // ring entries consumed by earlier items
         int ka = 0;             // items with work so far
+        int kfix = 0;           // items with a ragged tail so far
         int steps[2] = {0, 0};  // softmax steps of earlier items, per stage (barrier phase bookkeeping)
         for (int k = 0;; ++k) {
             const int id = get_work(k);
@@ -474,6 +479,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             // first QK^T of the next item may follow the last P V of this one directly.
             for (int it = 0; it <= w.n_tiles; ++it) {
                 if (it > 0) wait_full(ring + 2 * it - 1);
+                if (it == 1 && w.ragged_tail) mbar_wait(bar_vfix, kfix & 1);  // V rows past seqlen_k are zero now
                 if (it < w.n_tiles) wait_full(ring + 2 * it);
                 if (!DECODE && it == 0) mbar_wait(bar_q_full(1), ka & 1);
 #pragma unroll
@@ -515,6 +521,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             ring += 2 * w.n_tiles;
             steps[0] += w.it_hi[0] - w.it_lo[0];
             steps[1] += w.it_hi[1] - w.it_lo[1];
+            kfix += w.ragged_tail ? 1 : 0;
             ++ka;
         }
     } else if (warp < 8) {
@@ -781,8 +788,37 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 FA_TRACE_EV(220 + s);  // correction: epilogue of stage s stored
             }
         }
+    } else if (warp == 14) {
+        // ============================================================ V sanitiser
+        // P is exactly 0 for key columns past seqlen_k, but 0 * NaN = NaN: a KV cache is allowed to hold
+        // uninitialised memory beyond its valid length, and TMA cannot clip rows inside a tile. So for the one
+        // ragged tile of an item (always the first one processed) this warp zeroes the smem rows of V past
+        // seqlen_k before the MMA warp may read them. (K needs nothing: masked scores are replaced, not scaled.)
+        reg_dec<48>();
+        int ring = 0;
+        for (int k = 0;; ++k) {
+            const int id = get_work(k);
+            if (id >= total_work) break;
+            const WorkGeom w = work_geom<DECODE>(p, id);
+            if (w.n_tiles <= 0) continue;
+            if (w.ragged_tail) {
+                const int v_entry = ring + 1;
+                const int valid = w.g.seqlen_k - (w.n_max - 1) * BN;  // rows of the tail tile that hold keys
+                mbar_wait(bar_kv_full(v_entry % KV), (v_entry / KV) & 1);
+                const uint32_t v_smem = sKV + (v_entry % KV) * Cfg::kTileBytes;
+                // rows are 128 B long inside each 64-column block; the swizzle only permutes 16 B chunks in a row
+                for (int idx = lane; idx < (BN - valid) * 8 * (D / 64); idx += 32) {
+                    const int c16 = idx & 7, r = valid + ((idx >> 3) % (BN - valid)), blk = (idx >> 3) / (BN - valid);
+                    st_shared_v4(v_smem + blk * Cfg::kHalfBytes + r * 128 + c16 * 16, 0u, 0u, 0u, 0u);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_vfix);
+            }
+            ring += 2 * w.n_tiles;
+        }
     } else {
-        reg_dec<48>();  // warps 14, 15: spare
+        reg_dec<48>();  // warp 15: spare
     }
 
     // ------------------------------------------------------------------ teardown

@@ -454,3 +454,54 @@ def bwd(*args, **kwargs):
 
 def varlen_bwd(*args, **kwargs):
     raise NotImplementedError("backward is outside this build's scope (forward hot path only; SURVEY 8f rank 2)")
+
+
+# ======================================================================================
+# torch.ops.flash_attn_v100.* : the same five operators as dispatcher ops, with the reference's schemas
+# (reference kernel/fused_mha_api.cpp:308-358), so torch.compile / custom-op users find them.
+# ======================================================================================
+_OP_SCHEMAS = {
+    "fwd": "(Tensor(a!) q, Tensor k, Tensor v, Tensor? out, Tensor? alibi_slopes, float p_dropout, "
+           "float softmax_scale, bool is_causal, int window_left, int window_right, float softcap, "
+           "bool return_softmax, Generator? gen) -> Tensor[]",
+    "bwd": "(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor softmax_lse, Tensor? dq, Tensor? dk, "
+           "Tensor? dv, Tensor? alibi_slopes, float p_dropout, float softmax_scale, bool is_causal, int window_left, "
+           "int window_right, float softcap, bool deterministic, Generator? gen, Tensor? rng_state) -> Tensor[]",
+    "varlen_fwd": "(Tensor(a!) q, Tensor k, Tensor v, Tensor? out, Tensor cu_seqlens_q, Tensor cu_seqlens_k, "
+                  "Tensor? seqused_k, Tensor? leftpad_k, Tensor? block_table, Tensor? alibi_slopes, int max_seqlen_q, "
+                  "int max_seqlen_k, float p_dropout, float softmax_scale, bool zero_tensors, bool is_causal, "
+                  "int window_left, int window_right, float softcap, bool return_softmax, Generator? gen, "
+                  "int num_splits) -> Tensor[]",
+    "varlen_bwd": "(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor softmax_lse, Tensor? dq, Tensor? dk, "
+                  "Tensor? dv, Tensor cu_seqlens_q, Tensor cu_seqlens_k, Tensor? alibi_slopes, int max_seqlen_q, "
+                  "int max_seqlen_k, float p_dropout, float softmax_scale, bool zero_tensors, bool is_causal, "
+                  "int window_left, int window_right, float softcap, bool deterministic, Generator? gen, "
+                  "Tensor? rng_state) -> Tensor[]",
+    "fwd_kvcache": "(Tensor(a!) q, Tensor kcache, Tensor vcache, Tensor? k, Tensor? v, Tensor? seqlens_k, "
+                   "Tensor? rotary_cos, Tensor? rotary_sin, Tensor? cache_batch_idx, Tensor? leftpad_k, "
+                   "Tensor? block_table, Tensor? alibi_slopes, Tensor? out, float softmax_scale, bool is_causal, "
+                   "int window_left, int window_right, float softcap, bool is_rotary_interleaved, "
+                   "int num_splits) -> Tensor[]",
+}
+_ops_registered = False
+
+
+def register_torch_ops() -> bool:
+    """Define torch.ops.flash_attn_v100.{fwd,bwd,varlen_fwd,varlen_bwd,fwd_kvcache} (CUDA implementations
+    only: there is no CPU kernel to dispatch to). Returns False if the namespace is already taken
+    (e.g. the reference extension itself is loaded in this process)."""
+    global _ops_registered
+    if _ops_registered:
+        return True
+    impls = {"fwd": fwd, "bwd": bwd, "varlen_fwd": varlen_fwd, "varlen_bwd": varlen_bwd, "fwd_kvcache": fwd_kvcache}
+    try:
+        for name, schema in _OP_SCHEMAS.items():
+            torch.library.define(f"flash_attn_v100::{name}", schema)
+            torch.library.impl(f"flash_attn_v100::{name}", "CUDA")(impls[name])
+    except RuntimeError:
+        return False
+    _ops_registered = True
+    return True
+
+
+register_torch_ops()

@@ -148,3 +148,19 @@ def test_operator_layer_fails_loudly_without_cuda():
     q = torch.zeros(1, 2, 16, 64, dtype=torch.float16)
     with pytest.raises(RuntimeError, match="must be on CUDA"):
         op.fwd(q, q, q, None, None, 0.0, 1.0, False, -1, -1, 0.0, False, None)
+
+
+def test_torch_ops_are_registered_with_the_reference_schemas():
+    import torch
+
+    import flash_attn_v100_cuda as op
+
+    assert op.register_torch_ops()
+    for name in ("fwd", "bwd", "varlen_fwd", "varlen_bwd", "fwd_kvcache"):  # reference fused_mha_api.cpp:308-358
+        assert hasattr(torch.ops.flash_attn_v100, name)
+    schema = str(torch.ops.flash_attn_v100.fwd.default._schema)
+    assert "Tensor(a!) q" in schema and "Generator? gen" in schema and schema.endswith("-> Tensor[]")
+    assert len(torch.ops.flash_attn_v100.fwd_kvcache.default._schema.arguments) == 20
+    q = torch.zeros(1, 1, 16, 64, dtype=torch.float16)
+    with pytest.raises((NotImplementedError, RuntimeError)):  # no CPU kernel behind the op
+        torch.ops.flash_attn_v100.fwd(q, q, q, None, None, 0.0, 1.0, False, -1, -1, 0.0, False, None)

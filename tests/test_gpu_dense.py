@@ -202,3 +202,13 @@ def test_config5_window_slice_full_seqlen(api, op):
     out_, lse, _, _ = op.fwd(t(q), t(k), t(v), None, None, 0.0, D ** -0.5, True, 4096, 0, 0.0, False, None)
     rows = [(0, h, i) for h in (0, 3) for i in (0, 1, 4095, 4096, 4097, 5000, 8191, 4223, 4224)]
     sampled_row_check(t(out_), lse, q, k, v, rows, causal=True, window=(4096, 0))
+
+
+def test_dispatcher_op_matches_the_module_function(op):
+    """torch.ops.flash_attn_v100.fwd (reference kernel/fused_mha_api.cpp:308-315) runs the same kernel."""
+    torch.manual_seed(421)
+    q = torch.randn(1, 4, 256, 128, device="cuda", dtype=torch.bfloat16)
+    k, v = torch.randn_like(q), torch.randn_like(q)
+    a = op.fwd(q, k, v, None, None, 0.0, 128 ** -0.5, True, -1, -1, 0.0, False, None)
+    b = torch.ops.flash_attn_v100.fwd(q, k, v, None, None, 0.0, 128 ** -0.5, True, -1, -1, 0.0, False, None)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])

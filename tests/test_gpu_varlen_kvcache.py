@@ -217,3 +217,37 @@ def test_kvcache_argument_errors(op):
         op.fwd_kvcache(q, kc, kc, None, None, lens, None, None, lens, None, bt, None, None, 1.0, False, -1, -1, 0.0, True, 0)
     with pytest.raises(RuntimeError, match="softcap does not support window"):
         op.fwd_kvcache(q, kc, kc, None, None, lens, None, None, None, None, None, None, None, 1.0, False, 3, -1, 5.0, True, 0)
+
+
+@pytest.mark.parametrize("Sq", [1, 200])
+@pytest.mark.parametrize("paged", [False, True])
+def test_kvcache_rows_past_the_valid_length_may_hold_nan(api, Sq, paged):
+    """A cache is allowed to contain uninitialised memory beyond cache_seqlens: P is 0 there, but 0 * NaN
+    would poison P V unless the ragged V tile is sanitised (csrc/fwd_sm100.cuh, warp 14)."""
+    torch.manual_seed(5)
+    B, H, Hk, D, cap, page = 2, 8, 2, 128, 1024, 256
+    lens = torch.tensor([300, 777], dtype=torch.int32, device="cuda")
+    q = torch.randn(B, Sq, H, D, device="cuda", dtype=torch.bfloat16)
+    if paged:
+        kc = torch.randn(B * cap // page, page, Hk, D, device="cuda", dtype=torch.bfloat16)
+        vc = torch.randn_like(kc)
+        bt = torch.arange(B * cap // page, dtype=torch.int32, device="cuda").view(B, -1).flip(1).contiguous()
+        flat_k, flat_v = kc.view(-1, Hk, D), vc.view(-1, Hk, D)
+        for b in range(B):
+            for pg in range(cap // page):
+                lo = max(int(lens[b]) - pg * page, 0)
+                base = int(bt[b, pg]) * page
+                flat_k[base + lo: base + page] = float("nan")
+                flat_v[base + lo: base + page] = float("nan")
+    else:
+        kc = torch.randn(B, cap, Hk, D, device="cuda", dtype=torch.bfloat16)
+        vc = torch.randn_like(kc)
+        bt = None
+        for b in range(B):
+            kc[b, int(lens[b]):] = float("nan")
+            vc[b, int(lens[b]):] = float("nan")
+    out = api.flash_attn_with_kvcache(q, kc, vc, cache_seqlens=lens, block_table=bt, causal=True)
+    assert torch.isfinite(out.float()).all()
+    kz, vz = torch.nan_to_num(kc, nan=0.0), torch.nan_to_num(vc, nan=0.0)
+    ref, _, _, _ = ao.flash_attn_with_kvcache_ref(q, kz, vz, cache_seqlens=lens, block_table=bt, causal=True)
+    assert (out.double().cpu() - ref).abs().max().item() <= 2e-2
