@@ -749,6 +749,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 tc_fence_after();
                 FA_TRACE_EV(210 + s);  // correction: final O observed
                 const float inv = l > 0.f ? 1.0f / l : 0.f;
+                const bool wide_ok = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(dst) & 31) == 0);
                 if (partial_out) {
                     // split-KV partial: normalised fp32 O and this split's LSE; fa_combine_kernel merges them
                     const int64_t prow = (((int64_t)w.split * num_batch + w.batch) * p.num_heads + h_row) * w.g.seqlen_q + i_glob;
@@ -770,14 +771,16 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         float o[32];
                         tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
                         if (valid) {
+                            uint32_t pk[16];
 #pragma unroll
-                            for (int e = 0; e < 32; e += 8) {
-                                uint4 wv;
-                                wv.x = pack2<BF16>(o[e] * inv, o[e + 1] * inv);
-                                wv.y = pack2<BF16>(o[e + 2] * inv, o[e + 3] * inv);
-                                wv.z = pack2<BF16>(o[e + 4] * inv, o[e + 5] * inv);
-                                wv.w = pack2<BF16>(o[e + 6] * inv, o[e + 7] * inv);
-                                *reinterpret_cast<uint4*>(dst + c * 32 + e) = wv;
+                            for (int e = 0; e < 32; e += 2) pk[e / 2] = pack2<BF16>(o[e] * inv, o[e + 1] * inv);
+                            if (wide_ok) {  // 2 x 32 B per 32 columns instead of 4 x 16 B
+                                st_global_v8(dst + c * 32, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                                st_global_v8(dst + c * 32 + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 16; e += 4)
+                                    *reinterpret_cast<uint4*>(dst + c * 32 + 2 * e) = make_uint4(pk[e], pk[e + 1], pk[e + 2], pk[e + 3]);
                             }
                         }
                     }

@@ -115,6 +115,13 @@ FA_DEVICE void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int 
 FA_DEVICE void named_bar_sync(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+// 256-bit global store (sm_100): halves the LSU requests of row-per-thread epilogue stores; 32-byte aligned
+FA_DEVICE void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                            uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a), "r"(b), "r"(c),
+                 "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
+                 : "memory");
+}
 FA_DEVICE void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }

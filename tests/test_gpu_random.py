@@ -1,0 +1,109 @@
+"""Randomised GPU parity sweep: many small shape / feature combinations against the CPU oracle.
+
+Seeds are fixed, so failures reproduce; sizes are small enough for the float64 oracle to finish in milliseconds.
+Exercises the persistent scheduler with many work items of different lengths in one launch (ragged varlen
+batches, skipped blocks, empty key ranges) -- the situations the hand-picked cases may miss.
+"""
+import random
+
+import pytest
+import torch
+
+from oracle import attention_oracle as ao
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(fa_lib):
+    import flash_attn_v100 as m
+
+    return m
+
+
+def _tol(dtype):
+    return 2e-2 if dtype == torch.bfloat16 else 4e-3
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_dense(api, seed):
+    rng = random.Random(seed)
+    dtype = rng.choice([torch.float16, torch.bfloat16])
+    D = rng.choice([64, 128, 32, 96])
+    Hk = rng.choice([1, 2, 3])
+    H = Hk * rng.choice([1, 2, 4])
+    B = rng.randint(1, 3)
+    Sq = rng.choice([1, 7, 64, 128, 129, 255, 256, 257, 300, 513])
+    Sk = rng.choice([1, 5, 127, 128, 129, 256, 384, 511, 700])
+    causal = rng.random() < 0.5
+    window = rng.choice([(-1, -1), (-1, -1), (rng.randint(0, 300), rng.randint(0, 100)), (rng.randint(0, 200), -1)])
+    softcap = rng.choice([0.0, 0.0, 0.0, 25.0])
+    use_alibi = rng.random() < 0.25
+    torch.manual_seed(seed)
+    q = torch.randn(B, Sq, H, D, device="cuda", dtype=dtype)
+    k = torch.randn(B, Sk, Hk, D, device="cuda", dtype=dtype)
+    v = torch.randn(B, Sk, Hk, D, device="cuda", dtype=dtype)
+    slopes = (torch.rand(H, device="cuda") * 0.2).float() if use_alibi else None
+    out = api.flash_attn_func(q, k, v, causal=causal, window_size=window, softcap=softcap, alibi_slopes=slopes)
+    ref, _ = ao.flash_attn_func_ref(q, k, v, causal=causal, window_size=window, softcap=softcap, alibi_slopes=slopes)
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err <= _tol(dtype), (seed, err)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_varlen(api, seed):
+    rng = random.Random(1000 + seed)
+    dtype = rng.choice([torch.float16, torch.bfloat16])
+    D = rng.choice([64, 128])
+    Hk = rng.choice([1, 2])
+    H = Hk * rng.choice([1, 4])
+    nseq = rng.randint(1, 9)
+    lq = [rng.choice([1, 3, 64, 128, 200, 257, 600]) for _ in range(nseq)]
+    same = rng.random() < 0.5
+    lk = lq if same else [rng.choice([1, 17, 128, 129, 400, 900]) for _ in range(nseq)]
+    causal = rng.random() < 0.6
+    torch.manual_seed(seed)
+    q = torch.randn(sum(lq), H, D, device="cuda", dtype=dtype)
+    k = torch.randn(sum(lk), Hk, D, device="cuda", dtype=dtype)
+    v = torch.randn(sum(lk), Hk, D, device="cuda", dtype=dtype)
+    cq = torch.tensor([0] + list(torch.tensor(lq).cumsum(0)), dtype=torch.int32, device="cuda")
+    ck = torch.tensor([0] + list(torch.tensor(lk).cumsum(0)), dtype=torch.int32, device="cuda")
+    out = api.flash_attn_varlen_func(q, k, v, cq, ck, max(lq), max(lk), causal=causal)
+    ref, _ = ao.flash_attn_varlen_func_ref(q, k, v, cq, ck, max(lq), max(lk), causal=causal)
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err <= _tol(dtype), (seed, err)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_kvcache(api, seed):
+    rng = random.Random(2000 + seed)
+    dtype = rng.choice([torch.float16, torch.bfloat16])
+    D = rng.choice([64, 128])
+    Hk = rng.choice([1, 2, 4])
+    H = Hk * rng.choice([1, 2, 8])
+    B = rng.randint(1, 4)
+    Sq = rng.choice([1, 1, 2, 4, 16, 140])
+    cap = 768
+    paged = rng.random() < 0.5
+    causal = rng.random() < 0.7
+    lens = torch.tensor([rng.randint(0, cap - Sq) for _ in range(B)], dtype=torch.int32, device="cuda")
+    torch.manual_seed(seed)
+    q = torch.randn(B, Sq, H, D, device="cuda", dtype=dtype)
+    kn = torch.randn(B, Sq, Hk, D, device="cuda", dtype=dtype)
+    vn = torch.randn(B, Sq, Hk, D, device="cuda", dtype=dtype)
+    if paged:
+        npg = B * (cap // 256)
+        kc = torch.randn(npg, 256, Hk, D, device="cuda", dtype=dtype)
+        vc = torch.randn(npg, 256, Hk, D, device="cuda", dtype=dtype)
+        bt = torch.randperm(npg, generator=torch.Generator().manual_seed(seed)).view(B, -1).int().cuda()
+    else:
+        kc = torch.randn(B, cap, Hk, D, device="cuda", dtype=dtype)
+        vc = torch.randn(B, cap, Hk, D, device="cuda", dtype=dtype)
+        bt = None
+    ref, lse_ref, kc_ref, vc_ref = ao.flash_attn_with_kvcache_ref(q, kc, vc, kn, vn, cache_seqlens=lens, block_table=bt, causal=causal)
+    out, lse = api.flash_attn_with_kvcache(q, kc, vc, kn, vn, cache_seqlens=lens, block_table=bt, causal=causal,
+                                           return_softmax_lse=True)
+    assert torch.equal(kc.cpu(), kc_ref) and torch.equal(vc.cpu(), vc_ref)  # no rotary: the append is bit-exact
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err <= _tol(dtype), (seed, err)
+    assert (lse.double().cpu() - lse_ref).abs().max().item() < 3e-3
