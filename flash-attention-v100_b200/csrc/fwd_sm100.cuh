@@ -372,8 +372,17 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         int ring = 0;  // K of iteration it is ring entry (base + 2*it), V is (base + 2*it + 1)
         int ka = 0;    // items with work so far
         int id = DECODE ? 0 : (int)blockIdx.x;
+        auto fetch = [&]() -> int {  // next unclaimed work id (one atomic per CTA, broadcast to the warp)
+            int nid = 0;
+            if (lane == 0) nid = atomicAdd(p.sched, 1) + (int)gridDim.x;
+            return __shfl_sync(0xffffffffu, nid, 0);
+        };
         for (int k = 0;; ++k) {
             if constexpr (!DECODE) {
+                // Query blocks past the end of their sequence (the var-len grid is sized for the longest
+                // sequence) have nothing to compute or write: drop them here instead of sending every warp
+                // through a scheduler hand-shake for them.
+                while (id < total_work && work_geom<DECODE>(p, id).skip) id = fetch();
                 // publish the k-th work id (slot k&1 is free once everyone consumed item k-2)
                 if (k >= 2) mbar_wait(bar_sched_empty(k & 1), ((k >> 1) - 1) & 1);
                 if (lane == 0) {
@@ -387,10 +396,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             if (id >= total_work) break;
             const WorkGeom w = work_geom<DECODE>(p, id);
             int next_id = total_work;
-            if constexpr (!DECODE) {  // fetch the next item early: the atomic's latency hides behind the loads
-                if (lane == 0) next_id = atomicAdd(p.sched, 1) + (int)gridDim.x;
-                next_id = __shfl_sync(0xffffffffu, next_id, 0);
-            }
+            if constexpr (!DECODE) next_id = fetch();  // early: the atomic's latency hides behind the loads
             if (w.n_tiles > 0) {
                 auto kv_coords = [&](int n, int& row, int& b) {
                     const int r = n * BN;

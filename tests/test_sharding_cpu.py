@@ -82,3 +82,26 @@ def test_gloo_world2_max_reduce_and_gather():
 def test_single_process_paths():
     assert sharding.max_over_ranks(3.5) == 3.5
     assert sharding.gather_checksums(2.0) == [2.0]
+
+
+def test_bench_reference_arm_prints_one_json_line(tmp_path):
+    """`bench.py --impl reference` (CPU arm of the contract) on a shrunk workload: one JSON line, the
+    reference's own cpu_attention when oracle/_ref is built, else the C port."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--workload', 'c2']\n"
+        "import bench\n"
+        "bench.WORKLOADS['c2'] = dict(bench.WORKLOADS['c2'], seqlen=256, batch=1, heads=2, heads_k=2)\n"
+        "bench.main()\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "TFLOP/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
