@@ -212,3 +212,32 @@ def test_dispatcher_op_matches_the_module_function(op):
     a = op.fwd(q, k, v, None, None, 0.0, 128 ** -0.5, True, -1, -1, 0.0, False, None)
     b = torch.ops.flash_attn_v100.fwd(q, k, v, None, None, 0.0, 128 ** -0.5, True, -1, -1, 0.0, False, None)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_long_sequence_sampled_rows(api, op):
+    """S = 65536 (512 KV tiles per block, 256 work items per head): index arithmetic and the persistent
+    scheduler at a length far beyond the reference's own tests (max 8192, test.py:138)."""
+    B, S, H, D = 1, 65536, 2, 128
+    q, k, v = rand_qkv(B, S, S, H, 1, D, torch.bfloat16)
+    t = lambda x: x.permute(0, 2, 1, 3)
+    out_, lse, _, _ = op.fwd(t(q), t(k), t(v), None, None, 0.0, D ** -0.5, True, -1, -1, 0.0, False, None)
+    rows = [(0, 0, 0), (0, 1, 65535), (0, 0, 32767), (0, 1, 32768), (0, 0, 40001), (0, 1, 127), (0, 0, 65280)]
+    sampled_row_check(t(out_), lse, q, k, v, rows, causal=True)
+
+
+def test_concurrent_streams_use_separate_scheduler_slots(api):
+    """Two launches in flight on different streams must not share tile-scheduler state."""
+    q1, k1, v1 = rand_qkv(2, 2048, 2048, 8, 8, 128, torch.bfloat16, seed=1)
+    q2, k2, v2 = rand_qkv(4, 1024, 1024, 16, 4, 128, torch.bfloat16, seed=2)
+    ref1 = api.flash_attn_func(q1, k1, v1, causal=True)
+    ref2 = api.flash_attn_func(q2, k2, v2, causal=False)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs1, outs2 = [], []
+    for _ in range(10):
+        with torch.cuda.stream(s1):
+            outs1.append(api.flash_attn_func(q1, k1, v1, causal=True))
+        with torch.cuda.stream(s2):
+            outs2.append(api.flash_attn_func(q2, k2, v2, causal=False))
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, ref1) for o in outs1) and all(torch.equal(o, ref2) for o in outs2)
