@@ -95,10 +95,10 @@ int check_device(int device) {
     return 0;
 }
 
-template <int D, bool BF16, bool FEAT, bool DECODE = false>
+template <int D, bool BF16, bool FEAT, bool DECODE = false, bool DROPOUT = false>
 int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
     using Cfg = fa::FwdConfig<D>;
-    auto kern = fa::fa_fwd_sm100_kernel<D, BF16, FEAT, DECODE>;
+    auto kern = fa::fa_fwd_sm100_kernel<D, BF16, FEAT, DECODE, DROPOUT>;
     static std::once_flag once[64];
     int dev = 0;
     cudaGetDevice(&dev);
@@ -116,6 +116,12 @@ int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) 
 
 int launch_fwd(const fa::FwdKernelParams& kp, int head_dim, int dtype, bool feat, dim3 grid, cudaStream_t stream) {
     const bool bf16 = dtype == FA_B200_DTYPE_BF16;
+    if (kp.drop_thr != 0xffffffffu) {  // dropout on: one variant per (D, dtype), with the score-modifier path compiled in
+        if (head_dim == 128 && bf16) return launch_fwd_t<128, true, true, false, true>(kp, grid, stream);
+        if (head_dim == 128) return launch_fwd_t<128, false, true, false, true>(kp, grid, stream);
+        if (head_dim == 64 && bf16) return launch_fwd_t<64, true, true, false, true>(kp, grid, stream);
+        if (head_dim == 64) return launch_fwd_t<64, false, true, false, true>(kp, grid, stream);
+    }
 #define FA_CASE(DD, BB, FF) \
     if (head_dim == DD && bf16 == BB && feat == FF) return launch_fwd_t<DD, BB, FF>(kp, grid, stream);
     FA_CASE(128, true, false)
@@ -292,6 +298,33 @@ void fill_common(fa::FwdKernelParams& kp, const fa_b200_params_t* p, bool causal
     kp.window_left = wl;
     kp.window_right = causal ? 0 : wr;  // the causal mask is the right window of width 0
     kp.reverse_m = (kp.window_right >= 0 || kp.window_left >= 0) ? 1 : 0;
+    kp.rp_dropout = 1.0f;
+    kp.drop_thr = 0xffffffffu;  // keep everything
+}
+
+// Dropout state (reference include/softmax.h:50-51). `row_elems` = elements of one dmask row group.
+int fill_dropout(fa::FwdKernelParams& kp, const fa_b200_params_t* p, bool varlen) {
+    CHECK_ARG(p->p_dropout >= 0.f && p->p_dropout < 1.f, "p_dropout must be in [0, 1)");
+    if (p->p_dropout == 0.f) {
+        CHECK_ARG(p->dmask == nullptr, "return_softmax requires p_dropout > 0");
+        return 0;
+    }
+    CHECK_ARG(p->softcap == 0.f, "Softcapping does not support dropout");
+    kp.rp_dropout = 1.0f / (1.0f - p->p_dropout);
+    kp.drop_thr = static_cast<uint32_t>((1.0f - p->p_dropout) * 4294967295.0f);
+    kp.drop_seed = p->dropout_seed;
+    kp.drop_offset = p->dropout_offset;
+    kp.dmask = static_cast<uint16_t*>(p->dmask);
+    if (varlen) {  // (total_q, H, max_seqlen_k)   reference ..._varlen.cu:532
+        kp.dmask_stride_b = 0;
+        kp.dmask_stride_h = p->seqlen_k;
+        kp.dmask_stride_row = (int64_t)p->num_heads * p->seqlen_k;
+    } else {       // (B, H, Sq, Sk)               reference fused_mha_forward.cu:403
+        kp.dmask_stride_row = p->seqlen_k;
+        kp.dmask_stride_h = (int64_t)p->seqlen_q * p->seqlen_k;
+        kp.dmask_stride_b = (int64_t)p->num_heads * kp.dmask_stride_h;
+    }
+    return 0;
 }
 
 }  // namespace
@@ -347,6 +380,7 @@ FA_B200_API int fa_b200_fwd(const fa_b200_params_t* p, void* stream_v) {
     if (int rc = make_tmap(&kp.tm_k, p->dtype, p->k, p->head_dim, p->num_heads_k, p->seqlen_k, p->batch, p->k_stride_h, p->k_stride_s, p->k_stride_b, "k")) return rc;
     if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, p->seqlen_k, p->batch, p->v_stride_h, p->v_stride_s, p->v_stride_b, "v")) return rc;
 
+    if (int rc = fill_dropout(kp, p, false)) return rc;
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
     dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
     if (!kp.sched) return fail(FA_B200_EINVAL, "could not allocate the 8 KB tile-scheduler buffer on device %d", p->device);
@@ -399,6 +433,7 @@ FA_B200_API int fa_b200_varlen_fwd(const fa_b200_params_t* p, void* stream_v) {
         if (int rc = make_tmap(&kp.tm_k, p->dtype, p->k, p->head_dim, p->num_heads_k, p->total_k, 1, p->k_stride_h, p->k_stride_s, 0, "k")) return rc;
         if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, p->total_k, 1, p->v_stride_h, p->v_stride_s, 0, "v")) return rc;
     }
+    if (int rc = fill_dropout(kp, p, true)) return rc;
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
     dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
     if (!kp.sched) return fail(FA_B200_EINVAL, "could not allocate the 8 KB tile-scheduler buffer on device %d", p->device);
@@ -440,6 +475,7 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
         CHECK_ARG(p->workspace, "workspace is required when rotary is used (see fa_b200_workspace_bytes)");
     }
     CHECK_ARG(p->num_splits >= 0, "num_splits must be >= 0");
+    CHECK_ARG(p->p_dropout == 0.f && p->dmask == nullptr, "the kv-cache path has no dropout");
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail(FA_B200_EINVAL, "cannot select device %d", p->device);
 

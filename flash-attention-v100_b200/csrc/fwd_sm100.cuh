@@ -76,7 +76,38 @@ struct alignas(64) FwdKernelParams {
     // persistent tile scheduler (non-decode): sched[0] = next work item to hand out, sched[1] = CTAs done;
     // both are 0 before the launch and reset to 0 by the last CTA to finish.
     int* sched;
+    // dropout (reference include/softmax.h:96-125, include/philox.h): keep iff Philox word <= drop_thr;
+    // the 1/(1-p) factor is folded into the epilogue's 1/l. dmask: optional +-1.0 sign tensor.
+    float rp_dropout;       // 1 / (1 - p); 1 when dropout is off
+    uint32_t drop_thr;      // (1 - p) * (2^32 - 1), the reference's float expression
+    uint64_t drop_seed;
+    uint64_t drop_offset;
+    uint16_t* dmask;
+    int64_t dmask_stride_b, dmask_stride_h, dmask_stride_row;  // elements; row = q_off + position
 };
+
+// Philox4x32-10 (reference include/philox.h:13-64): counter = (c0, c1, 0, 0), key = (k0, k1).
+FA_DEVICE uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+    uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+        x0 = hi1 ^ x1 ^ k0;
+        x1 = lo1;
+        x2 = hi0 ^ x3 ^ k1;
+        x3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(x0, x1, x2, x3);
+}
+
+// Keep bits of the 4 flat indices {4g .. 4g+3} (bit t = index 4g+t is kept).
+FA_DEVICE uint32_t philox_keep4(uint64_t ctr, uint32_t k0, uint32_t k1, uint32_t thr) {
+    const uint4 r = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), k0, k1);
+    return (r.x <= thr ? 1u : 0u) | (r.y <= thr ? 2u : 0u) | (r.z <= thr ? 4u : 0u) | (r.w <= thr ? 8u : 0u);
+}
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -272,7 +303,7 @@ FA_DEVICE WorkGeom work_geom(const FwdKernelParams& p, int work_id) {
 // DECODE = true : grid (KV splits, KV heads, batch), one item per CTA; ONE tile whose 128 rows are the
 //                 (position, head) pairs of a whole GQA group (row = position * G + head_in_group), so a
 //                 decode step reads each K/V byte once per group; only stage 0 runs. HBM-bound by construction.
-template <int D, bool BF16, bool FEAT, bool DECODE = false>
+template <int D, bool BF16, bool FEAT, bool DECODE = false, bool DROPOUT = false>
 __global__ void __launch_bounds__(512, 1)
 fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     using Cfg = FwdConfig<D>;
@@ -567,6 +598,16 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             float m_ref = -INFINITY;  // running reference max (raw score units; log2 units if FEAT)
             float row_sum = 0.f;
 
+            // dropout: flat index of (this row, column 0) in the reference's numbering, and the dmask row
+            uint64_t drop_row_idx = 0;
+            uint16_t* dm_row = nullptr;
+            if constexpr (DROPOUT) {
+                drop_row_idx = (uint64_t)(w.g.q_off + i_glob) * (uint64_t)p.seqlen_k;
+                if (p.dmask && i_glob < w.g.seqlen_q)
+                    dm_row = p.dmask + w.o_b * p.dmask_stride_b + w.head * p.dmask_stride_h +
+                             (int64_t)(w.g.q_off + i_glob) * p.dmask_stride_row;
+            }
+
             for (int j = 0; j < my_n; ++j) {
                 const int j0 = (w.n_max - 1 - (my_lo + j)) * BN;
                 mbar_wait(bar_s_full(s), (steps + j) & 1);
@@ -628,6 +669,19 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
 #pragma unroll
                 for (int ch = 0; ch < BN / 32; ++ch) {
                     uint32_t pk[16];
+                    uint32_t keep = 0xffffffffu;  // bit c = column ch*32+c survives dropout
+                    if constexpr (DROPOUT) {
+                        // counter = offset + (flat index >> 2), word = flat index & 3 (reference softmax.h:97-104)
+                        const uint64_t idx0 = drop_row_idx + (uint64_t)(j0 + ch * 32);
+                        const uint32_t sh = (uint32_t)idx0 & 3u;
+                        const uint64_t ctr0 = p.drop_offset + (idx0 >> 2);
+                        const uint32_t k0 = (uint32_t)p.drop_seed, k1 = (uint32_t)(p.drop_seed >> 32);
+                        uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) lo |= philox_keep4(ctr0 + g, k0, k1, p.drop_thr) << (4 * g);
+                        if (sh != 0u) hi = philox_keep4(ctr0 + 8, k0, k1, p.drop_thr);
+                        keep = __funnelshift_r(lo, hi, sh);
+                    }
 #pragma unroll
                     for (int c = 0; c < 32; c += 2) {
                         float p0 = v[ch * 32 + c], p1 = v[ch * 32 + c + 1];
@@ -638,8 +692,34 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                             p0 = ex2_approx(p0);
                             p1 = ex2_approx(p1);
                         }
-                        add2(sum0, sum1, p0, p1);
+                        add2(sum0, sum1, p0, p1);  // the row sum uses P before dropout (reference softmax.h:94)
+                        if constexpr (DROPOUT) {
+                            p0 = (keep >> c) & 1u ? p0 : 0.f;
+                            p1 = (keep >> (c + 1)) & 1u ? p1 : 0.f;
+                        }
                         pk[c / 2] = pack2<BF16>(p0, p1);
+                    }
+                    if constexpr (DROPOUT) {
+                        if (dm_row) {  // +1.0 kept / -1.0 dropped (reference softmax.h:116-124), columns < seqlen_k only
+                            constexpr uint32_t kOne2 = BF16 ? 0x3F803F80u : 0x3C003C00u;
+                            const int c_base = j0 + ch * 32;
+                            uint16_t* dm = dm_row + c_base;
+                            const bool vec_ok = (reinterpret_cast<uintptr_t>(dm) & 15) == 0;
+#pragma unroll
+                            for (int c = 0; c < 32; c += 8) {
+                                uint32_t wd[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    wd[e] = kOne2 | (((~keep >> (c + 2 * e)) & 1u) << 15) | (((~keep >> (c + 2 * e + 1)) & 1u) << 31);
+                                if (vec_ok && c_base + c + 8 <= w.g.seqlen_k) {
+                                    *reinterpret_cast<uint4*>(dm + c) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e)
+                                        if (c_base + c + e < w.g.seqlen_k) dm[c + e] = (uint16_t)(wd[e >> 1] >> (16 * (e & 1)));
+                                }
+                            }
+                        }
                     }
                     tmem_st_x16(tP + ch * 16, pk);
                     if (FA_SPLIT_P && ch == BN / 32 - 2) {  // 3/4 of P is on its way: let P V start
@@ -754,7 +834,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 mbar_wait(bar_o_full(s), items[s] & 1);
                 tc_fence_after();
                 FA_TRACE_EV(210 + s);  // correction: final O observed
-                const float inv = l > 0.f ? 1.0f / l : 0.f;
+                const float inv = l > 0.f ? (DROPOUT ? p.rp_dropout : 1.0f) / l : 0.f;
                 const bool wide_ok = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(dst) & 31) == 0);
                 if (partial_out) {
                     // split-KV partial: normalised fp32 O and this split's LSE; fa_combine_kernel merges them

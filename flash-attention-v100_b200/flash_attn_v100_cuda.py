@@ -69,6 +69,8 @@ class FaB200Params(ctypes.Structure):
         ("softmax_scale", _f32), ("softcap", _f32),
         ("is_causal", _i32), ("window_left", _i32), ("window_right", _i32), ("num_splits", _i32),
         ("workspace", _ptr), ("workspace_bytes", _i64),
+        ("p_dropout", _f32), ("reserved3", _i32), ("dropout_seed", ctypes.c_uint64), ("dropout_offset", ctypes.c_uint64),
+        ("dmask", _ptr),
     ]
 
 
@@ -99,8 +101,8 @@ def load_library() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [ctypes.POINTER(FaB200Params), ctypes.c_void_p]
-    if lib.fa_b200_abi_version() != 1:
-        raise ImportError(f"libfa_b200.so ABI {lib.fa_b200_abi_version()} != 1")
+    if lib.fa_b200_abi_version() != 2:
+        raise ImportError(f"libfa_b200.so ABI {lib.fa_b200_abi_version()} != 2")
     _lib = lib
     return lib
 
@@ -169,13 +171,25 @@ def _alibi(p: FaB200Params, alibi_slopes: Optional[torch.Tensor], batch: int, he
     keep.append(s)
 
 
-def _no_dropout(p_dropout: float, return_softmax: bool, softcap: float) -> None:
+def _check_dropout(p_dropout: float, return_softmax: bool, softcap: float) -> None:
     _check(0.0 <= p_dropout < 1.0, "p_dropout must be in [0, 1)")
     if softcap > 0.0:
         _check(p_dropout == 0.0, "Softcapping does not support dropout")
     _check((not return_softmax) or p_dropout > 0.0, "return_softmax requires p_dropout > 0")
-    if p_dropout > 0.0:
-        raise NotImplementedError("dropout in the forward is not built yet (SURVEY 8f rank 1)")
+
+
+def _dropout_state(p: FaB200Params, p_dropout: float, gen_, device: torch.device, batch: int, heads: int) -> torch.Tensor:
+    """Seed / offset from the CUDA generator, advanced like the reference does
+    (kernel/fused_mha_forward.cu:373-386): offset += B * H * 32. Returns rng_state = [seed, offset] (int64)."""
+    if p_dropout <= 0.0:
+        return torch.empty((2,), dtype=torch.int64, device=device)  # only meaningful with dropout
+    gen = gen_ if gen_ is not None else torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed, offset = int(gen.initial_seed()), int(gen.get_offset())
+    gen.set_offset(offset + batch * heads * 32)
+    seed &= 2 ** 64 - 1
+    p.p_dropout, p.dropout_seed, p.dropout_offset = float(p_dropout), seed, offset
+    as_i64 = lambda x: x - 2 ** 64 if x >= 2 ** 63 else x  # rng_state is int64 like the reference's
+    return torch.tensor([as_i64(seed), as_i64(offset)], dtype=torch.int64).to(device, non_blocking=True)
 
 
 # ======================================================================================
@@ -191,12 +205,14 @@ def fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, windo
     Hk, N = k.shape[1], k.shape[2]
     _check(B > 0, "batch size must be positive")
     _check(H % Hk == 0, "H_Q must be divisible by H_K for GQA/MQA")
-    _no_dropout(p_dropout, return_softmax, softcap)
+    _check_dropout(p_dropout, return_softmax, softcap)
     Dp = _padded_dim(D)
 
     lse = torch.empty((B, H, M), dtype=torch.float32, device=q.device)
-    dmask = torch.empty((0,), dtype=q.dtype, device=q.device)
-    rng_state = torch.empty((2,), dtype=torch.int64, device=q.device)  # only meaningful with dropout
+    want_mask = return_softmax and p_dropout > 0.0  # reference :401-406
+    # +1 kept / -1 dropped wherever the kernel evaluated the score tile; 0 in tiles it skipped (fully masked)
+    dmask = torch.zeros((B, H, M, N), dtype=q.dtype, device=q.device) if want_mask else torch.empty((0,), dtype=q.dtype, device=q.device)
+    rng_state = None
     if out_ is not None:
         _check(out_.dtype == q.dtype, "out must have the same dtype as q")
         _check(out_.is_cuda, "out must be on CUDA")
@@ -206,7 +222,7 @@ def fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, windo
         out = out_ if out_ is not None else torch.empty_like(q)
         out.zero_()
         lse.fill_(float("-inf"))
-        return [out, lse, dmask, rng_state]
+        return [out, lse, dmask, torch.empty((2,), dtype=torch.int64, device=q.device)]
 
     qp, kp, vp = (_aligned(_pad_last(t, Dp)) for t in (q, k, v))
     direct = out_ is not None and Dp == D and _aligned(out_) is out_
@@ -227,6 +243,9 @@ def fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, windo
     _alibi(p, alibi_slopes_, B, H, keep)
     p.softmax_scale, p.softcap = float(softmax_scale), float(softcap)
     p.is_causal, p.window_left, p.window_right = int(bool(is_causal)), int(window_left), int(window_right)
+    rng_state = _dropout_state(p, p_dropout, gen_, q.device, B, H)
+    if want_mask:
+        p.dmask = dmask.data_ptr()
     _call("fa_b200_fwd", p, q.device)
 
     if not direct:
@@ -271,11 +290,13 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k_, leftpad_k_
     if seqused_k_ is not None:
         _check(seqused_k_.dtype == torch.int32 and seqused_k_.is_cuda and seqused_k_.is_contiguous()
                and seqused_k_.numel() == B, "seqused_k must be a contiguous int32 CUDA tensor of size batch")
-    _no_dropout(p_dropout, return_softmax, softcap)
+    _check_dropout(p_dropout, return_softmax, softcap)
     Dp = _padded_dim(D)
 
     lse = torch.empty((H, T), dtype=torch.float32, device=q.device)
-    dmask = torch.empty((0,), dtype=q.dtype, device=q.device)
+    want_mask = return_softmax and p_dropout > 0.0  # reference ..._varlen.cu:530-534
+    dmask = (torch.zeros((T, H, int(max_seqlen_k)), dtype=q.dtype, device=q.device) if want_mask
+             else torch.empty((0,), dtype=q.dtype, device=q.device))
     rng_state = torch.empty((2,), dtype=torch.int64, device=q.device)  # only meaningful with dropout
     if out_ is not None:
         _check(out_.dtype == q.dtype and out_.is_cuda and out_.stride(-1) == 1 and out_.shape == q.shape,
@@ -319,6 +340,9 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k_, leftpad_k_
     p.softmax_scale, p.softcap = float(softmax_scale), float(softcap)
     p.is_causal, p.window_left, p.window_right = int(bool(is_causal)), int(window_left), int(window_right)
     p.num_splits = int(num_splits)
+    rng_state = _dropout_state(p, p_dropout, gen_, q.device, B, H)
+    if want_mask:
+        p.dmask = dmask.data_ptr()
     _call("fa_b200_varlen_fwd", p, q.device)
 
     if not direct:

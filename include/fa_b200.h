@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FA_B200_ABI_VERSION 1
+#define FA_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FA_B200_API __attribute__((visibility("default")))
@@ -133,6 +133,16 @@ typedef struct fa_b200_params {
     /* scratch for split-KV partial results; see fa_b200_workspace_bytes */
     void* workspace;
     int64_t workspace_bytes;
+
+    /* dropout (dense and varlen; reference include/softmax.h:96-125, include/philox.h:59-119):
+     * element (row, col) is kept iff word[(idx & 3)] of Philox4x32-10(key = seed, counter = offset + (idx >> 2))
+     * is <= (1 - p) * (2^32 - 1), with idx = row * dropout_cols + col; kept P is scaled by 1/(1-p), the row
+     * sum uses P before dropout. As in the reference the index ignores batch and head. */
+    float p_dropout;       /* 0 = off */
+    int32_t reserved3;
+    uint64_t dropout_seed;
+    uint64_t dropout_offset;
+    void* dmask;           /* optional: +1.0 kept / -1.0 dropped in q's dtype; dense (B,H,Sq,Sk), varlen (total_q,H,max_seqlen_k) */
 } fa_b200_params_t;
 
 /* kinds for fa_b200_workspace_bytes */

@@ -64,10 +64,52 @@ def normalize_mask_args(seqlen_q: int, seqlen_k: int, causal: bool, window: Tupl
     return wl, wr
 
 
+# ----------------------------------------------------------------------------- dropout (Philox4x32-10)
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+_U32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(counter_lo64: np.ndarray, key: int, counter_hi64: int = 0) -> np.ndarray:
+    """Philox4x32-10 (Salmon et al., SC'11; reference include/philox.h:13-64). `counter_lo64`: uint64 array
+    holding counter words (x, y); `counter_hi64` words (z, w); `key` 64-bit. Returns uint32 [..., 4]."""
+    c = np.asarray(counter_lo64, dtype=np.uint64)
+    x0, x1 = c & _U32, c >> np.uint64(32)
+    x2 = np.full_like(x0, counter_hi64 & 0xFFFFFFFF)
+    x3 = np.full_like(x0, (counter_hi64 >> 32) & 0xFFFFFFFF)
+    k0, k1 = key & 0xFFFFFFFF, (key >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = _PHILOX_M0 * x0, _PHILOX_M1 * x2          # 32x32 -> 64 bit, exact in uint64
+        x0, x1, x2, x3 = ((p1 >> np.uint64(32)) ^ x1 ^ np.uint64(k0), p1 & _U32,
+                          (p0 >> np.uint64(32)) ^ x3 ^ np.uint64(k1), p0 & _U32)
+        k0, k1 = (k0 + _PHILOX_W0) & 0xFFFFFFFF, (k1 + _PHILOX_W1) & 0xFFFFFFFF
+    return np.stack([x0, x1, x2, x3], axis=-1).astype(np.uint32)
+
+
+def dropout_keep_mask(p_dropout: float, seed: int, offset: int, row0: int, rows: int, cols: int,
+                      row_len: int) -> torch.Tensor:
+    """bool [rows, cols]: element (row0 + r, c) survives. Reference include/softmax.h:50-51,96-109: flat index
+    idx = row * row_len + col (no batch / head term), counter = offset + (idx >> 2), word = idx & 3, keep iff
+    word <= uint32((1 - p) * 4294967295.0f) evaluated in float32. (For row_len % 4 != 0 the reference reuses one
+    counter for 4 consecutive columns of a row; this restatement -- and the CUDA path -- use the pure
+    function of idx, identical whenever row_len % 4 == 0, the only case the reference's dense path handles.)"""
+    thr = int(np.uint32(np.float32(np.float32(1.0) - np.float32(p_dropout)) * np.float32(4294967295.0)))
+    r = np.arange(rows, dtype=np.uint64).reshape(-1, 1) + np.uint64(row0)
+    idx = r * np.uint64(row_len) + np.arange(cols, dtype=np.uint64).reshape(1, -1)
+    ctr = (np.uint64(offset) + (idx >> np.uint64(2))).reshape(-1)
+    uniq, inv = np.unique(ctr, return_inverse=True)
+    words = philox4x32_10(uniq, seed & (2 ** 64 - 1))[inv.reshape(-1)]
+    sel = np.take_along_axis(words, (idx.reshape(-1, 1) & np.uint64(3)).astype(np.int64), axis=1).reshape(rows, cols)
+    return torch.from_numpy(sel <= np.uint32(thr))
+
+
 def attention_one(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, wl: int, wr: int,
                   slopes: Optional[torch.Tensor], softcap: float,
-                  dtype=torch.float64) -> Tuple[torch.Tensor, torch.Tensor]:
-    """One sequence. q:[Sq,H,D] k,v:[Sk,Hk,D] -> out [Sq,H,D] (dtype), lse [H,Sq] (dtype)."""
+                  dtype=torch.float64, keep: Optional[torch.Tensor] = None,
+                  p_dropout: float = 0.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One sequence. q:[Sq,H,D] k,v:[Sk,Hk,D] -> out [Sq,H,D] (dtype), lse [H,Sq] (dtype).
+    `keep` [Sq,Sk] bool + p_dropout: dropped P entries are zeroed, kept ones scaled by 1/(1-p); the
+    normaliser l and the LSE use P before dropout (reference include/softmax.h:94,111-114)."""
     Sq, H, D = q.shape
     Sk, Hk, _ = k.shape
     g = H // Hk
@@ -97,6 +139,8 @@ def attention_one(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: floa
     m_safe = torch.where(has_key, m, torch.zeros_like(m))
     p = torch.exp(s - m_safe.unsqueeze(-1))
     l = p.sum(dim=-1)
+    if keep is not None:
+        p = p * keep.to(dtype).view(1, Sq, Sk) / (1.0 - p_dropout)
     o = torch.einsum("hqk,khd->qhd", p, vf)
     l_safe = torch.where(has_key, l, torch.ones_like(l))
     out = o / l_safe.t().unsqueeze(-1)
@@ -113,8 +157,9 @@ def _slopes_for(alibi_slopes: Optional[torch.Tensor], b: int) -> Optional[torch.
 
 
 def flash_attn_func_ref(q, k, v, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
-                        alibi_slopes=None, dtype=torch.float64):
-    """Dense. q:(B,Sq,H,D) k,v:(B,Sk,Hk,D) -> out (B,Sq,H,D), lse (B,H,Sq)."""
+                        alibi_slopes=None, dtype=torch.float64, dropout_p=0.0, rng_state=None):
+    """Dense. q:(B,Sq,H,D) k,v:(B,Sk,Hk,D) -> out (B,Sq,H,D), lse (B,H,Sq).
+    dropout_p > 0 needs rng_state = (seed, offset); every (batch, head) shares one mask, as in the reference."""
     q, k, v = q.detach().cpu(), k.detach().cpu(), v.detach().cpu()
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
@@ -122,9 +167,13 @@ def flash_attn_func_ref(q, k, v, softmax_scale=None, causal=False, window_size=(
     if Sk == 0:  # reference kernel/fused_mha_forward.cu:409-413
         return torch.zeros((B, Sq, H, D), dtype=dtype), torch.full((B, H, Sq), float("-inf"), dtype=dtype)
     wl, wr = normalize_mask_args(Sq, Sk, causal, window_size, alibi_slopes is not None)
+    keep = None
+    if dropout_p > 0.0:
+        keep = dropout_keep_mask(dropout_p, int(rng_state[0]), int(rng_state[1]), 0, Sq, Sk, Sk)
     outs, lses = [], []
     for b in range(B):
-        o, l = attention_one(q[b], k[b], v[b], scale, wl, wr, _slopes_for(alibi_slopes, b), softcap, dtype)
+        o, l = attention_one(q[b], k[b], v[b], scale, wl, wr, _slopes_for(alibi_slopes, b), softcap, dtype,
+                             keep, dropout_p)
         outs.append(o)
         lses.append(l)
     return torch.stack(outs), torch.stack(lses)
@@ -142,8 +191,10 @@ def _gather_paged(cache: torch.Tensor, block_table_row: torch.Tensor, length: in
 
 def flash_attn_varlen_func_ref(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
                                softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
-                               alibi_slopes=None, block_table=None, seqused_k=None, dtype=torch.float64):
-    """Packed. q:(T,H,D); k,v:(Tk,Hk,D) or paged (num_pages,page,Hk,D) -> out (T,H,D), lse (H,T)."""
+                               alibi_slopes=None, block_table=None, seqused_k=None, dtype=torch.float64,
+                               dropout_p=0.0, rng_state=None):
+    """Packed. q:(T,H,D); k,v:(Tk,Hk,D) or paged (num_pages,page,Hk,D) -> out (T,H,D), lse (H,T).
+    Dropout index: row = packed q row, row length = max_seqlen_k (reference ..._varlen.cu:235)."""
     q, k, v = q.detach().cpu(), k.detach().cpu(), v.detach().cpu()
     cu_q = cu_seqlens_q.detach().cpu().long()
     cu_k = cu_seqlens_k.detach().cpu().long()
@@ -173,7 +224,11 @@ def flash_attn_varlen_func_ref(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q
             kb, vb = _gather_paged(k, bt, lk), _gather_paged(v, bt, lk)
         else:
             kb, vb = k[ks:ks + lk], v[ks:ks + lk]
-        o, l = attention_one(q[qs:qe], kb, vb, scale, wl, wr, _slopes_for(alibi_slopes, b), softcap, dtype)
+        keep = None
+        if dropout_p > 0.0 and qe > qs and lk > 0:
+            keep = dropout_keep_mask(dropout_p, int(rng_state[0]), int(rng_state[1]), qs, qe - qs, lk, int(max_seqlen_k))
+        o, l = attention_one(q[qs:qe], kb, vb, scale, wl, wr, _slopes_for(alibi_slopes, b), softcap, dtype,
+                             keep, dropout_p)
         out[qs:qe] = o
         lse[:, qs:qe] = l
     return out, lse

@@ -11,7 +11,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "fa_b200.h")
 
-C2CT = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float}
+C2CT = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "uint64_t": ctypes.c_uint64}
 
 
 def _header_fields():
@@ -60,7 +60,7 @@ def test_library_exports_every_declared_symbol(fa_lib):
     assert sorted(declared) == sorted(op.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(fa_lib, name) is not None
-    assert fa_lib.fa_b200_abi_version() == 1
+    assert fa_lib.fa_b200_abi_version() == 2
     assert fa_lib.fa_b200_launch_count() == 0
 
 

@@ -158,10 +158,8 @@ def test_empty_kv_and_errors(op, api):
         op.fwd(q.float(), q.float(), q.float(), None, None, 0.0, 1.0, False, -1, -1, 0.0, False, None)
     with pytest.raises(RuntimeError, match="divisible"):
         op.fwd(torch.zeros(1, 3, 8, 64, device="cuda", dtype=torch.float16), q, q, None, None, 0.0, 1.0, False, -1, -1, 0.0, False, None)
-    with pytest.raises(NotImplementedError):
-        api.flash_attn_func(q.permute(0, 2, 1, 3), q.permute(0, 2, 1, 3), q.permute(0, 2, 1, 3), dropout_p=0.1)
-    with pytest.raises(NotImplementedError):
-        op.bwd()
+    with pytest.raises(RuntimeError, match="Softcapping does not support dropout"):
+        api.flash_attn_func(q.permute(0, 2, 1, 3), q.permute(0, 2, 1, 3), q.permute(0, 2, 1, 3), dropout_p=0.1, softcap=10.0)
 
 
 def test_config2_full_size_properties(api, op):

@@ -219,3 +219,45 @@ def test_tolerance_rule_is_the_references():
     assert not ok
     ok, _, _ = ao.fa_tolerance_ok(torch.tensor([float("nan"), 0, 0, 0]), ref, naive)
     assert not ok
+
+
+# ----------------------------------------------------------------------------- dropout (Philox)
+def test_philox4x32_10_known_answers():
+    """Random123 known-answer vectors for philox4x32-10 (kat_vectors of the published library): pins the
+    generator the reference re-implements in include/philox.h."""
+    import numpy as np
+
+    def run(c, k):
+        lo = np.array([c[0] | (c[1] << 32)], dtype=np.uint64)
+        return [int(x) for x in ao.philox4x32_10(lo, k[0] | (k[1] << 32), c[2] | (c[3] << 32))[0]]
+
+    assert run([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert run([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert run([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == \
+        [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_dropout_keep_mask_properties():
+    m = ao.dropout_keep_mask(0.25, 1234, 8, 0, 256, 512, 512)
+    assert abs(m.float().mean().item() - 0.75) < 0.01
+    # pure function of the flat index: a row offset of r equals starting r rows later
+    m2 = ao.dropout_keep_mask(0.25, 1234, 8, 100, 50, 512, 512)
+    assert torch.equal(m[100:150], m2)
+    # counter offset of 1 = 4 flat indices
+    m3 = ao.dropout_keep_mask(0.25, 1234, 9, 0, 1, 508, 512)
+    assert torch.equal(m3[0], m[0, 4:])
+    assert not torch.equal(ao.dropout_keep_mask(0.25, 1235, 8, 0, 8, 64, 64), m[:8, :64])
+
+
+def test_dropout_oracle_is_unbiased_and_keeps_lse():
+    torch.manual_seed(0)
+    q, k, v = (torch.randn(1, 64, 2, 32) for _ in range(3))
+    base, lse0 = ao.flash_attn_func_ref(q, k, v, causal=True)
+    acc = torch.zeros_like(base)
+    n = 200
+    for t in range(n):
+        o, lse = ao.flash_attn_func_ref(q, k, v, causal=True, dropout_p=0.3, rng_state=(7, 4096 * t))
+        assert torch.equal(lse, lse0)
+        acc += o
+    assert (acc / n - base).abs().max().item() < 0.35  # Monte-Carlo mean of 200 masks
+    assert (acc / n - base).abs().mean().item() < 0.05
