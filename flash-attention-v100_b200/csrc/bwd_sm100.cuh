@@ -1,0 +1,595 @@
+// Fused attention backward for sm_100a:  dQ, dK, dV from dO, Q, K, V, LSE and delta = rowsum(dO * O).
+//
+// What it replaces: the reference's backward kernels
+//   flash_attention_backward_kernel          (reference kernel/fused_mha_backward.cu:26-505)
+//   flash_attention_backward_varlen_kernel   (reference kernel/fused_mha_backward_varlen.cu)
+// and their building blocks (row dot include/product.h:9-96, softmax gradient include/softmax.h:205-406,
+// gradient GEMMs include/mat_mul.h:166-234). The reference runs two phases in one grid -- phase 1: one CTA per
+// query block accumulates dQ over the KV tiles; phase 2: one CTA per KV block (per KV head, looping over the GQA
+// group) accumulates dK and dV over the query tiles -- each recomputing S and dP, so no atomics are needed and
+// the result is deterministic. That two-pass structure is kept (it is the right one for an exact drop-in:
+// deterministic, no fp32 dQ workspace), the schedule is Blackwell-native:
+//
+//   * one kernel template, two instantiations: KV_STAT = false is the dQ pass, KV_STAT = true the dK/dV pass.
+//     The "stationary" block (128 rows of Q+dO, or of K+V) sits in smem for the whole CTA, the other side
+//     streams through a TMA ring in 128-row tiles.
+//   * per streamed tile:  T1 = A1 B1^T  (S or S^T),  T2 = A2 B2^T  (dP or dP^T)   -- tcgen05.mma SS form
+//                         P  = exp2(T1 * scale * log2e - lse * log2e),  dS = P * (dP - delta)
+//                         out1 += dS B1   (dQ += dS K   /  dK += dS^T Q)          -- TS form, A read from TMEM
+//                         out2 += P  B2   (             /  dV += P^T dO)
+//     All accumulators live in TMEM: T1 [0,128) T2 [128,256) out1 [256,256+D) out2 [256+D,256+2D).
+//     P (16-bit) is written back over T1, dS over T2, each warpgroup into the columns it read itself.
+//   * warps 0-7: element-wise stage; thread == TMEM lane (a row of the stationary block); warpgroup 0 takes tile
+//     columns [0,64), warpgroup 1 [64,128). Per-row statistics (dQ pass) are registers, per-column statistics
+//     (dK/dV pass) come from a double-buffered smem table filled by the same warps.
+//   * warp 8: TMA producer.  warp 9: tcgen05.mma issuer.  mbarriers order everything.
+//
+// The softmax scale is applied in the epilogue (dQ, dK *= scale), and so is dropout's 1/(1-p) on dV.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+
+#include "fwd_sm100.cuh"
+
+namespace fa {
+
+struct alignas(64) BwdKernelParams {
+    CUtensorMap tm_q;   // 4-D (head_dim, heads, rows, batch), box (64, 1, 128, 1), 128B swizzle
+    CUtensorMap tm_k;
+    CUtensorMap tm_v;
+    CUtensorMap tm_do;
+    void* dq;
+    void* dk;
+    void* dv;
+    int64_t dq_stride_b, dq_stride_s, dq_stride_h;  // elements
+    int64_t dk_stride_b, dk_stride_s, dk_stride_h;
+    int64_t dv_stride_b, dv_stride_s, dv_stride_h;
+    const float* lse;    // forward LSE (natural log); [B,H,Sq] or var-len [H,T]
+    const float* delta;  // rowsum(dO * O), same layout as lse
+    int64_t lse_stride_b, lse_stride_h;
+    const int* cu_seqlens_q;
+    const int* cu_seqlens_k;
+    const float* alibi;
+    int64_t alibi_stride_b;
+    int seqlen_q;  // dense Sq / var-len max_seqlen_q
+    int seqlen_k;  // dense Sk / var-len max_seqlen_k (also the dropout row length)
+    int num_heads;
+    int heads_per_kv;
+    float scale;
+    float scale_log2;
+    float softcap;
+    int window_left;   // -1 = unbounded
+    int window_right;  // -1 = unbounded; causal is window_right = 0
+    float rp_dropout;
+    uint32_t drop_thr;
+    uint64_t drop_seed;
+    uint64_t drop_offset;
+    int num_blocks;  // stationary blocks along the sequence (grid.x)
+    int reverse;     // launch the last block first (dQ pass with a causal / right-window mask)
+};
+
+template <int D>
+struct BwdConfig {
+    static constexpr int kTileBytes = 128 * D * 2;
+    static constexpr int kHalfBytes = 128 * 128;
+    static constexpr int kRing = (D == 128) ? 4 : 6;  // streamed tiles in flight (B1, B2 alternate)
+    static constexpr int kSmemStat = 2 * kTileBytes;
+    static constexpr int kSmemRing = kRing * kTileBytes;
+    static constexpr int kNumBars = 2 + 2 * kRing + 5;
+    static constexpr int kOffBars = kSmemStat + kSmemRing;
+    static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
+    static constexpr int kOffStats = (kOffTmemPtr + 16 + 15) & ~15;  // float [2 buffers][2 kinds][128]
+    static constexpr int kSmemUsed = kOffStats + 2 * 2 * 128 * 4;
+    static constexpr int kSmemBytes = kSmemUsed + 1024;
+    static constexpr int kTmemT1 = 0, kTmemT2 = 128, kTmemOut1 = 256, kTmemOut2 = 256 + D;
+};
+
+FA_DEVICE void mul2(float& a0, float& a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\t"
+        "mul.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
+
+FA_DEVICE uint32_t pack_half2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+FA_DEVICE float2 unpack_half2(uint32_t v) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+
+// LSE as the kernel uses it: -lse * log2(e); rows without any visible key (sentinel / -inf) get a finite value
+// (all of their scores are masked, so P is 0 whatever it is).
+FA_DEVICE float neg_lse_log2(float lse) {
+    return (lse > -1e29f && lse < 1e30f) ? -lse * kLog2e : 0.f;
+}
+
+// delta[row] = sum_d O[row, d] * dO[row, d] in fp32 (reference include/product.h:9-96). One warp per
+// (batch, head, position) row; this is also the `softmax_d` tensor the operator returns.
+template <bool BF16>
+__global__ void fa_bwd_dot_kernel(const uint16_t* __restrict__ o, const uint16_t* __restrict__ dout,
+                                  float* __restrict__ delta, int head_dim, int64_t rows_total, int seqlen_q,
+                                  int heads, int64_t o_sb, int64_t o_ss, int64_t o_sh, int64_t do_sb, int64_t do_ss,
+                                  int64_t do_sh, int64_t d_sb, int64_t d_sh) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows_total) return;
+    // row enumerates (b, s, h) with h fastest: neighbouring warps read neighbouring heads of one token
+    const int h = (int)(row % heads);
+    const int64_t bs = row / heads;
+    const int s = (int)(bs % seqlen_q);
+    const int64_t b = bs / seqlen_q;
+    const uint16_t* po = o + b * o_sb + (int64_t)s * o_ss + (int64_t)h * o_sh;
+    const uint16_t* pd = dout + b * do_sb + (int64_t)s * do_ss + (int64_t)h * do_sh;
+    float acc = 0.f;
+    for (int c = lane * 8; c < head_dim; c += 256) {
+        const uint4 a = *reinterpret_cast<const uint4*>(po + c);
+        const uint4 g = *reinterpret_cast<const uint4*>(pd + c);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 x, y;
+            if constexpr (BF16) {
+                x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[e]));
+                y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
+            } else {
+                x = __half22float2(*reinterpret_cast<const __half2*>(&aw[e]));
+                y = __half22float2(*reinterpret_cast<const __half2*>(&gw[e]));
+            }
+            acc = fmaf(x.x, y.x, acc);
+            acc = fmaf(x.y, y.y, acc);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) delta[b * d_sb + (int64_t)h * d_sh + s] = acc;
+}
+
+template <int D, bool BF16, bool FEAT, bool KV_STAT, bool DROPOUT>
+__global__ void __launch_bounds__(384, 1)
+fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
+    using Cfg = BwdConfig<D>;
+    constexpr int BT = 128;  // tile rows on both sides
+    constexpr int RING = Cfg::kRing;
+
+    // ------------------------------------------------------------------ geometry (uniform over the CTA)
+    const int batch = blockIdx.z;
+    int q_off = 0, q_b = batch, seqlen_q = p.seqlen_q, k_off = 0, k_b = batch, seqlen_k = p.seqlen_k;
+    if (p.cu_seqlens_q) {
+        q_off = p.cu_seqlens_q[batch];
+        seqlen_q = p.cu_seqlens_q[batch + 1] - q_off;
+        q_b = 0;
+        k_off = p.cu_seqlens_k[batch];
+        seqlen_k = p.cu_seqlens_k[batch + 1] - k_off;
+        k_b = 0;
+    }
+    const int o_b = p.cu_seqlens_q ? 0 : batch;
+    const int G = p.heads_per_kv;
+    const int off = seqlen_k - seqlen_q;
+    const int blk = p.reverse ? p.num_blocks - 1 - (int)blockIdx.x : (int)blockIdx.x;
+    const int x0 = blk * BT;  // first row of the stationary block (query position or key position)
+    if (x0 >= (KV_STAT ? seqlen_k : seqlen_q)) return;
+    const int kv_head = KV_STAT ? (int)blockIdx.y : (int)blockIdx.y / G;
+    const int head0 = KV_STAT ? kv_head * G : (int)blockIdx.y;  // first (dK/dV pass) or only (dQ pass) query head
+
+    // streamed tiles [t_lo, t_hi) along the other sequence, visible to at least one row of this block
+    int t_lo = 0, t_hi;
+    if constexpr (KV_STAT) {
+        t_hi = (seqlen_q + BT - 1) / BT;
+        const int j_last = min(x0 + BT, seqlen_k) - 1;
+        if (p.window_right >= 0) t_lo = max(0, x0 - off - p.window_right) / BT;
+        if (p.window_left >= 0) {
+            const int i_max = j_last - off + p.window_left;
+            t_hi = min(t_hi, i_max < 0 ? 0 : i_max / BT + 1);
+        }
+    } else {
+        t_hi = (seqlen_k + BT - 1) / BT;
+        const int i_last = min(x0 + BT, seqlen_q) - 1;
+        if (p.window_right >= 0) {
+            const int j_max = i_last + off + p.window_right;
+            t_hi = min(t_hi, j_max < 0 ? 0 : j_max / BT + 1);
+        }
+        if (p.window_left >= 0) t_lo = max(0, x0 + off - p.window_left) / BT;
+    }
+    const int nt = max(t_hi - t_lo, 0);         // tiles per head
+    const int n_tiles = KV_STAT ? nt * G : nt;  // the dK/dV pass streams the whole GQA group
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_raw_u32 = smem_u32(smem_raw);
+    const uint32_t sbase = (smem_raw_u32 + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_raw_u32);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const uint32_t sStat = sbase;                   // A1, A2
+    const uint32_t sRing = sbase + Cfg::kSmemStat;  // B tiles
+    const uint32_t bars = sbase + Cfg::kOffBars;
+    auto bar_a_full = [&](int s) { return bars + 8 * s; };
+    auto bar_ring_full = [&](int i) { return bars + 8 * (2 + i); };
+    auto bar_ring_empty = [&](int i) { return bars + 8 * (2 + RING + i); };
+    constexpr int kB0 = 2 + 2 * RING;
+    const uint32_t bar_t1_full = bars + 8 * (kB0 + 0);   // MMA -> element-wise: T1 ready
+    const uint32_t bar_t2_full = bars + 8 * (kB0 + 1);   // MMA -> element-wise: T2 ready
+    const uint32_t bar_p_ready = bars + 8 * (kB0 + 2);   // element-wise -> MMA: T1 consumed (and P written)
+    const uint32_t bar_ds_ready = bars + 8 * (kB0 + 3);  // element-wise -> MMA: dS written over T2
+    const uint32_t bar_out_full = bars + 8 * (kB0 + 4);  // MMA -> epilogue: accumulators final
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffTmemPtr);
+    float* sTab = reinterpret_cast<float*>(sgen + Cfg::kOffStats);
+
+    if (warp == 8 && lane == 0) {
+        mbar_init(bar_a_full(0), 1);
+        mbar_init(bar_a_full(1), 1);
+        for (int i = 0; i < RING; ++i) {
+            mbar_init(bar_ring_full(i), 1);
+            mbar_init(bar_ring_empty(i), 1);
+        }
+        mbar_init(bar_t1_full, 1);
+        mbar_init(bar_t2_full, 1);
+        mbar_init(bar_p_ready, 8);
+        mbar_init(bar_ds_ready, 8);
+        mbar_init(bar_out_full, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&p.tm_q);
+        tma_prefetch_desc(&p.tm_k);
+        tma_prefetch_desc(&p.tm_v);
+        tma_prefetch_desc(&p.tm_do);
+    }
+    if (warp == 9) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 8) {
+        // ============================================================ TMA producer
+        reg_dec<48>();
+        if (n_tiles > 0) {
+            auto load_tile = [&](const CUtensorMap* tm, uint32_t dst, uint32_t bar, int h, int row, int b) {
+                mbar_arrive_expect_tx(bar, Cfg::kTileBytes);
+#pragma unroll
+                for (int c = 0; c < D / 64; ++c) tma_load_4d(dst + c * Cfg::kHalfBytes, tm, bar, c * 64, h, row, b);
+            };
+            int ring = 0;
+            auto produce = [&](const CUtensorMap* tm, int h, int row, int b) {
+                const int slot = ring % RING;
+                mbar_wait(bar_ring_empty(slot), ((ring / RING) & 1) ^ 1);
+                if (lane == 0) load_tile(tm, sRing + slot * Cfg::kTileBytes, bar_ring_full(slot), h, row, b);
+                ++ring;
+            };
+            auto stream_tile = [&](int t, bool second) {
+                const int g = KV_STAT ? t / nt : 0;
+                const int ti = t_lo + (KV_STAT ? t - g * nt : t);
+                if constexpr (KV_STAT) produce(second ? &p.tm_do : &p.tm_q, head0 + g, q_off + ti * BT, q_b);
+                else produce(second ? &p.tm_v : &p.tm_k, kv_head, k_off + ti * BT, k_b);
+            };
+            if (lane == 0) {
+                if constexpr (KV_STAT) load_tile(&p.tm_k, sStat, bar_a_full(0), kv_head, k_off + x0, k_b);
+                else load_tile(&p.tm_q, sStat, bar_a_full(0), head0, q_off + x0, q_b);
+            }
+            stream_tile(0, false);
+            if (lane == 0) {
+                if constexpr (KV_STAT) load_tile(&p.tm_v, sStat + Cfg::kTileBytes, bar_a_full(1), kv_head, k_off + x0, k_b);
+                else load_tile(&p.tm_do, sStat + Cfg::kTileBytes, bar_a_full(1), head0, q_off + x0, q_b);
+            }
+            stream_tile(0, true);
+            for (int t = 1; t < n_tiles; ++t) {
+                stream_tile(t, false);
+                stream_tile(t, true);
+            }
+        }
+    } else if (warp == 9) {
+        // ============================================================ MMA issuer
+        reg_dec<48>();
+        if (n_tiles > 0) {
+            constexpr uint32_t idesc_t = umma_idesc_f16(BF16, BT, BT, false, false);
+            constexpr uint32_t idesc_o = umma_idesc_f16(BF16, BT, D, false, true);
+            const uint32_t tT1 = tmem_base + Cfg::kTmemT1, tT2 = tmem_base + Cfg::kTmemT2;
+            const uint32_t tO1 = tmem_base + Cfg::kTmemOut1, tO2 = tmem_base + Cfg::kTmemOut2;
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t kLoKmajor = 1u << 16;
+            constexpr uint32_t kLoMn = (uint32_t)(Cfg::kHalfBytes >> 4) << 16;
+            auto lo_addr = [](uint32_t saddr) { return (saddr & 0x3FFFFu) >> 4; };
+            auto slot_addr = [&](int r) { return sRing + (r % RING) * Cfg::kTileBytes; };
+            auto wait_full = [&](int r) { mbar_wait(bar_ring_full(r % RING), (r / RING) & 1); };
+            auto issue_t = [&](uint32_t d_tmem, int a_idx, int r) {  // d = A[a_idx] * B(ring r)^T
+                const uint32_t a_lo = lo_addr(sStat + a_idx * Cfg::kTileBytes) | kLoKmajor;
+                const uint32_t b_lo = lo_addr(slot_addr(r)) | kLoKmajor;
+                if constexpr (D == 128) umma_issue_qk_d128(d_tmem, a_lo, b_lo, kDescHi, kDescHi, idesc_t);
+                else umma_issue_qk_d64(d_tmem, a_lo, b_lo, kDescHi, kDescHi, idesc_t);
+            };
+            mbar_wait(bar_a_full(0), 0);
+            wait_full(0);
+            tc_fence_after();
+            issue_t(tT1, 0, 0);
+            umma_commit_elect(bar_t1_full);
+            mbar_wait(bar_a_full(1), 0);
+            wait_full(1);
+            tc_fence_after();
+            issue_t(tT2, 1, 1);
+            umma_commit_elect(bar_t2_full);
+            for (int t = 0; t < n_tiles; ++t) {
+                const uint32_t ph = t & 1;
+                mbar_wait(bar_p_ready, ph);  // T1(t) is in registers; in the dK/dV pass P(t) sits in T1's columns
+                tc_fence_after();
+                if constexpr (KV_STAT)
+                    umma_issue_ts_split(tO2, tT1, lo_addr(slot_addr(2 * t + 1)) | kLoMn, 0, kDescHi, idesc_o, t > 0 ? 1u : 0u);
+                if (t + 1 < n_tiles) {  // executes after the P read above (tcgen05 ops run in issue order)
+                    wait_full(2 * t + 2);
+                    tc_fence_after();
+                    issue_t(tT1, 0, 2 * t + 2);
+                    umma_commit_elect(bar_t1_full);
+                }
+                mbar_wait(bar_ds_ready, ph);
+                tc_fence_after();
+                umma_issue_ts_split(tO1, tT2, lo_addr(slot_addr(2 * t)) | kLoMn, 0, kDescHi, idesc_o, t > 0 ? 1u : 0u);
+                umma_commit_elect(bar_ring_empty((2 * t) % RING));
+                umma_commit_elect(bar_ring_empty((2 * t + 1) % RING));
+                if (t + 1 < n_tiles) {
+                    wait_full(2 * t + 3);
+                    tc_fence_after();
+                    issue_t(tT2, 1, 2 * t + 3);
+                    umma_commit_elect(bar_t2_full);
+                }
+            }
+            umma_commit_elect(bar_out_full);
+        }
+    } else if (warp < 8) {
+        // ============================================================ element-wise stage + epilogue
+        reg_inc<216>();
+        const int wg = warp >> 2;                  // column half of every tile
+        const int r = (warp & 3) * 32 + lane;      // row of the stationary block == TMEM lane
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tT1 = tmem_base + lane_off + Cfg::kTmemT1 + wg * 64;
+        const uint32_t tT2 = tmem_base + lane_off + Cfg::kTmemT2 + wg * 64;
+        const int x = x0 + r;  // this thread's query position (dQ pass) or key position (dK/dV pass)
+        const float sl2 = FEAT ? 1.0f : p.scale_log2;
+
+        // visible range [lo, lo + width) of the streamed index for this row
+        int lo = 0, hi;
+        if constexpr (KV_STAT) {
+            hi = seqlen_q;
+            if (p.window_right >= 0) lo = max(0, x - off - p.window_right);
+            if (p.window_left >= 0) hi = min(hi, x - off + p.window_left + 1);
+            if (x >= seqlen_k) hi = lo;
+        } else {
+            hi = seqlen_k;
+            if (p.window_right >= 0) hi = min(hi, x + off + p.window_right + 1);
+            if (p.window_left >= 0) lo = max(0, x + off - p.window_left);
+            if (x >= seqlen_q) hi = lo;
+        }
+        const unsigned width = (unsigned)max(hi - lo, 0);
+
+        float row_nl = 0.f, row_delta = 0.f;  // dQ pass: this row's -lse*log2e and delta
+        if constexpr (!KV_STAT) {
+            if (x < seqlen_q) {
+                const int64_t idx = o_b * p.lse_stride_b + (int64_t)head0 * p.lse_stride_h + q_off + x;
+                row_nl = neg_lse_log2(p.lse[idx]);
+                row_delta = p.delta[idx];
+            }
+        }
+        const float inv_cap = (FEAT && p.softcap > 0.f) ? 1.0f / p.softcap : 0.f;
+
+        // dK/dV pass: column statistics of streamed tile t, one value per thread (256 threads = 128 x {lse, delta})
+        auto load_stat = [&](int t) -> float {
+            const int g = t / max(nt, 1);
+            const int i = (t_lo + t - g * nt) * BT + (threadIdx.x & 127);
+            if (t >= n_tiles || i >= seqlen_q) return 0.f;
+            const int64_t idx = o_b * p.lse_stride_b + (int64_t)(head0 + g) * p.lse_stride_h + q_off + i;
+            return threadIdx.x < 128 ? neg_lse_log2(p.lse[idx]) : -p.delta[idx];
+        };
+        float stat_next = 0.f;
+        if constexpr (KV_STAT) stat_next = load_stat(0);
+
+        for (int t = 0; t < n_tiles; ++t) {
+            const int g = KV_STAT ? t / nt : 0;
+            const int c0 = (t_lo + (KV_STAT ? t - g * nt : t)) * BT + wg * 64;  // streamed index of my first column
+            const float* tab = sTab + (t & 1) * 256;
+            if constexpr (KV_STAT) {
+                sTab[(t & 1) * 256 + threadIdx.x] = stat_next;
+                named_bar_sync(1, 256);
+                stat_next = load_stat(t + 1);
+            }
+            float slope = 0.f;
+            if constexpr (FEAT) {
+                if (p.alibi) slope = p.alibi[batch * p.alibi_stride_b + head0 + g];
+            }
+
+            // ---- T1 -> P
+            mbar_wait(bar_t1_full, t & 1);
+            tc_fence_after();
+            float pv[64];
+            tmem_ld_x64_wait(tT1, reinterpret_cast<uint32_t*>(pv));
+            if constexpr (!KV_STAT) {  // dQ pass: nothing is written back over T1, release it right away
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_p_ready);
+            }
+            uint32_t fac[FEAT ? 32 : 1];  // softcap: (1 - tanh^2) as f16 pairs
+            if constexpr (FEAT) {
+                // reference order (include/mat_mul.h:111-117): scale, ALiBi, softcap
+                const int rel0 = KV_STAT ? c0 + off - x : x + off - c0;  // i + off - j at column 0
+#pragma unroll
+                for (int c = 0; c < 64; c += 2) {
+                    float u[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        u[e] = pv[c + e] * p.scale - slope * fabsf((float)(KV_STAT ? rel0 + c + e : rel0 - c - e));
+                        float f = 1.0f;
+                        if (p.softcap > 0.f) {
+                            const float th = tanh_approx(u[e] * inv_cap);
+                            u[e] = p.softcap * th;
+                            f = fmaf(-th, th, 1.0f);  // reference include/softmax.h:307-310
+                        }
+                        pv[c + e] = u[e] * kLog2e;
+                        u[e] = f;
+                    }
+                    fac[c / 2] = pack_half2(u[0], u[1]);
+                }
+            }
+            const bool need_mask = (c0 < lo) || ((unsigned)(c0 + 64 - lo) > width);
+            if (__any_sync(0xffffffffu, need_mask)) {
+                const int base = c0 - lo;
+#pragma unroll
+                for (int c = 0; c < 64; ++c) pv[c] = ((unsigned)(base + c) < width) ? pv[c] : -INFINITY;
+            }
+#pragma unroll
+            for (int c = 0; c < 64; c += 4) {
+                float n0, n1, n2, n3;
+                if constexpr (KV_STAT) {
+                    const float4 nl = *reinterpret_cast<const float4*>(tab + wg * 64 + c);
+                    n0 = nl.x, n1 = nl.y, n2 = nl.z, n3 = nl.w;
+                } else {
+                    n0 = n1 = n2 = n3 = row_nl;
+                }
+                fma2(pv[c], pv[c + 1], sl2, sl2, n0, n1);
+                fma2(pv[c + 2], pv[c + 3], sl2, sl2, n2, n3);
+                pv[c] = ex2_approx(pv[c]);
+                pv[c + 1] = ex2_approx(pv[c + 1]);
+                pv[c + 2] = ex2_approx(pv[c + 2]);
+                pv[c + 3] = ex2_approx(pv[c + 3]);
+            }
+            // dropout keep bits for my 64 columns (reference include/softmax.h:276-291: same index as the forward)
+            uint32_t keep[2] = {0xffffffffu, 0xffffffffu};
+            if constexpr (DROPOUT) {
+                const uint32_t k0 = (uint32_t)p.drop_seed, k1 = (uint32_t)(p.drop_seed >> 32);
+                if constexpr (KV_STAT) {  // columns are query rows: every element has its own counter
+#pragma unroll 1
+                    for (int w = 0; w < 2; ++w) {
+                        uint32_t bits = 0u;
+#pragma unroll 4
+                        for (int c = 0; c < 32; ++c) {
+                            const uint64_t idx = (uint64_t)(q_off + c0 + w * 32 + c) * (uint64_t)p.seqlen_k + (uint64_t)x;
+                            const uint32_t k4 = philox_keep4(p.drop_offset + (idx >> 2), k0, k1, p.drop_thr);
+                            bits |= ((k4 >> ((uint32_t)idx & 3u)) & 1u) << c;
+                        }
+                        keep[w] = bits;
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const uint64_t idx0 = (uint64_t)(q_off + x) * (uint64_t)p.seqlen_k + (uint64_t)(c0 + w * 32);
+                        const uint32_t sh = (uint32_t)idx0 & 3u;
+                        const uint64_t ctr0 = p.drop_offset + (idx0 >> 2);
+                        uint32_t lo_w = 0u, hi_w = 0u;
+#pragma unroll
+                        for (int q4 = 0; q4 < 8; ++q4) lo_w |= philox_keep4(ctr0 + q4, k0, k1, p.drop_thr) << (4 * q4);
+                        if (sh != 0u) hi_w = philox_keep4(ctr0 + 8, k0, k1, p.drop_thr);
+                        keep[w] = __funnelshift_r(lo_w, hi_w, sh);
+                    }
+                }
+            }
+            if constexpr (KV_STAT) {  // P (after dropout, unscaled) -> TMEM over my half of T1
+                uint32_t pk[32];
+#pragma unroll
+                for (int c = 0; c < 64; c += 2) {
+                    float a = pv[c], b = pv[c + 1];
+                    if constexpr (DROPOUT) {
+                        a = (keep[c >> 5] >> (c & 31)) & 1u ? a : 0.f;
+                        b = (keep[c >> 5] >> ((c + 1) & 31)) & 1u ? b : 0.f;
+                    }
+                    pk[c / 2] = pack2<BF16>(a, b);
+                }
+                tmem_st_x32(tT1, pk);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_p_ready);
+            }
+
+            // ---- T2 -> dS = P * (keep * rp * dP - delta)       (reference include/softmax.h:293-294)
+            mbar_wait(bar_t2_full, t & 1);
+            tc_fence_after();
+            uint32_t dsk[32];
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+                float dp[32];
+                tmem_ld_x32_wait(tT2 + hc * 32, reinterpret_cast<uint32_t*>(dp));
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const int cc = hc * 32 + c;
+                    float a = dp[c], b = dp[c + 1];
+                    if constexpr (DROPOUT) {
+                        a = (keep[hc] >> c) & 1u ? a * p.rp_dropout : 0.f;
+                        b = (keep[hc] >> (c + 1)) & 1u ? b * p.rp_dropout : 0.f;
+                    }
+                    float d0, d1;
+                    if constexpr (KV_STAT) {
+                        const float2 nd = *reinterpret_cast<const float2*>(tab + 128 + wg * 64 + cc);
+                        d0 = nd.x, d1 = nd.y;
+                    } else {
+                        d0 = d1 = -row_delta;
+                    }
+                    add2(a, b, d0, d1);
+                    mul2(a, b, pv[cc], pv[cc + 1]);
+                    if constexpr (FEAT) {
+                        const float2 f = unpack_half2(fac[cc / 2]);
+                        mul2(a, b, f.x, f.y);
+                    }
+                    dsk[cc / 2] = pack2<BF16>(a, b);
+                }
+            }
+            tmem_st_x32(tT2, dsk);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ds_ready);
+        }
+
+        // ---- epilogue: warpgroup wg stores columns [wg*D/2, (wg+1)*D/2) of each accumulator
+        const bool row_ok = x < (KV_STAT ? seqlen_k : seqlen_q);
+        if (n_tiles > 0) {
+            mbar_wait(bar_out_full, 0);
+            tc_fence_after();
+        }
+        constexpr int HALF = D / 2;
+        auto store_out = [&](uint32_t tmem_col, void* base, int64_t sb, int64_t ss, int64_t sh, int head, int row_off,
+                             float mult) {
+            uint16_t* dst = static_cast<uint16_t*>(base) + o_b * sb + (int64_t)(row_off + x) * ss + (int64_t)head * sh + wg * HALF;
+            const bool wide_ok = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(dst) & 31) == 0);
+#pragma unroll
+            for (int c = 0; c < HALF; c += 32) {
+                float o[32];
+                if (n_tiles > 0) {
+                    tmem_ld_x32_wait(tmem_base + lane_off + tmem_col + wg * HALF + c, reinterpret_cast<uint32_t*>(o));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) o[e] = 0.f;
+                }
+                if (row_ok) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) pk[e / 2] = pack2<BF16>(o[e] * mult, o[e + 1] * mult);
+                    if (wide_ok) {
+                        st_global_v8(dst + c, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                        st_global_v8(dst + c + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4)
+                            *reinterpret_cast<uint4*>(dst + c + 2 * e) = make_uint4(pk[e], pk[e + 1], pk[e + 2], pk[e + 3]);
+                    }
+                }
+            }
+        };
+        if constexpr (KV_STAT) {
+            store_out(Cfg::kTmemOut1, p.dk, p.dk_stride_b, p.dk_stride_s, p.dk_stride_h, kv_head, k_off, p.scale);
+            store_out(Cfg::kTmemOut2, p.dv, p.dv_stride_b, p.dv_stride_s, p.dv_stride_h, kv_head, k_off,
+                      DROPOUT ? p.rp_dropout : 1.0f);
+        } else {
+            store_out(Cfg::kTmemOut1, p.dq, p.dq_stride_b, p.dq_stride_s, p.dq_stride_h, head0, q_off, p.scale);
+        }
+    } else {
+        reg_dec<48>();  // warps 10, 11: idle (they complete the third warpgroup for setmaxnreg)
+    }
+
+    // ------------------------------------------------------------------ teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace fa

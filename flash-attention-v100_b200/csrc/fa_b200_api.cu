@@ -15,6 +15,7 @@
 
 #include "../../include/fa_b200.h"
 #include "fwd_sm100.cuh"
+#include "bwd_sm100.cuh"
 #include "kvcache_prep.cuh"
 
 namespace {
@@ -600,5 +601,166 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
     if (!kp.sched) return fail(FA_B200_EINVAL, "could not allocate the 8 KB tile-scheduler buffer on device %d", p->device);
     return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
 }
+
+// ------------------------------------------------------------------------------------------ backward
+}  // extern "C"
+
+namespace {
+
+template <int D, bool BF16, bool FEAT, bool KV_STAT, bool DROPOUT>
+int launch_bwd_t(const fa::BwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+    using Cfg = fa::BwdConfig<D>;
+    auto kern = fa::fa_bwd_sm100_kernel<D, BF16, FEAT, KV_STAT, DROPOUT>;
+    static std::once_flag once[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t attr_err = cudaSuccess;
+    std::call_once(once[dev & 63], [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    });
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(smem)");
+    kern<<<grid, 384, Cfg::kSmemBytes, stream>>>(kp);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fa_bwd_sm100_kernel launch");
+    return 0;
+}
+
+template <bool KV_STAT>
+int launch_bwd(const fa::BwdKernelParams& kp, int head_dim, bool bf16, bool feat, bool dropout, dim3 grid, cudaStream_t stream) {
+    // dropout variants are built with the score-modifier path compiled in (one variant per D and dtype)
+#define FA_BCASE(DD, BB)                                                                                       \
+    if (head_dim == DD && bf16 == BB) {                                                                        \
+        if (dropout) return launch_bwd_t<DD, BB, true, KV_STAT, true>(kp, grid, stream);                       \
+        if (feat) return launch_bwd_t<DD, BB, true, KV_STAT, false>(kp, grid, stream);                         \
+        return launch_bwd_t<DD, BB, false, KV_STAT, false>(kp, grid, stream);                                  \
+    }
+    FA_BCASE(128, true)
+    FA_BCASE(128, false)
+    FA_BCASE(64, true)
+    FA_BCASE(64, false)
+#undef FA_BCASE
+    return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (64 and 128 are)", head_dim);
+}
+
+int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
+    g_err[0] = 0;
+    if (int rc = check_common(p)) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    // reference kernel/fused_mha_backward.cu:604-700
+    CHECK_ARG(p->dout && p->dq && p->dk && p->dv && p->softmax_d, "dout, dq, dk, dv and softmax_d must be non-NULL");
+    CHECK_ARG(p->seqlen_q > 0 && p->seqlen_k > 0, "seqlen_q / seqlen_k must be positive (the caller handles empty inputs)");
+    CHECK_ARG(p->p_dropout >= 0.f && p->p_dropout < 1.f, "p_dropout must be in [0, 1)");
+    CHECK_ARG(p->softcap == 0.f || p->p_dropout == 0.f, "Softcapping does not support dropout");
+    CHECK_ARG(p->block_table == nullptr, "the backward has no paged-KV form");
+    auto aligned16 = [](const void* ptr, int64_t a, int64_t b, int64_t c) {
+        return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && a % 8 == 0 && b % 8 == 0 && c % 8 == 0;
+    };
+    CHECK_ARG(aligned16(p->dq, p->dq_stride_b, p->dq_stride_s, p->dq_stride_h) &&
+                  aligned16(p->dk, p->dk_stride_b, p->dk_stride_s, p->dk_stride_h) &&
+                  aligned16(p->dv, p->dv_stride_b, p->dv_stride_s, p->dv_stride_h),
+              "dq, dk, dv must be 16-byte aligned with strides that are multiples of 8 elements");
+    CHECK_ARG(aligned16(p->out, p->o_stride_b, p->o_stride_s, p->o_stride_h) &&
+                  aligned16(p->dout, p->do_stride_b, p->do_stride_s, p->do_stride_h),
+              "out and dout must be 16-byte aligned with strides that are multiples of 8 elements");
+    if (varlen) {
+        CHECK_ARG(p->cu_seqlens_q && p->cu_seqlens_k, "cu_seqlens_q and cu_seqlens_k are required");
+        CHECK_ARG(p->total_q > 0 && p->total_k > 0, "total_q and total_k must be positive");
+    }
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(FA_B200_EINVAL, "cannot select device %d", p->device);
+
+    // the same normalisations as the forward (reference kernel/fused_mha_backward.cu:636-641)
+    bool causal = p->is_causal != 0;
+    if (p->seqlen_q == 1 && !p->alibi_slopes) causal = false;
+    int wl = p->window_left, wr = p->window_right;
+    if (wl >= p->seqlen_k) wl = -1;
+    if (wr >= p->seqlen_k) wr = -1;
+    if (causal) wr = 0;
+    const bool bf16 = p->dtype == FA_B200_DTYPE_BF16;
+
+    fa::BwdKernelParams kp;
+    memset(&kp, 0, sizeof(kp));
+    const int64_t rows_q = varlen ? p->total_q : p->seqlen_q;
+    const int64_t rows_k = varlen ? p->total_k : p->seqlen_k;
+    const int64_t nb = varlen ? 1 : p->batch;
+    if (int rc = make_tmap(&kp.tm_q, p->dtype, p->q, p->head_dim, p->num_heads, rows_q, nb, p->q_stride_h, p->q_stride_s, varlen ? 0 : p->q_stride_b, "q")) return rc;
+    if (int rc = make_tmap(&kp.tm_do, p->dtype, p->dout, p->head_dim, p->num_heads, rows_q, nb, p->do_stride_h, p->do_stride_s, varlen ? 0 : p->do_stride_b, "dout")) return rc;
+    if (int rc = make_tmap(&kp.tm_k, p->dtype, p->k, p->head_dim, p->num_heads_k, rows_k, nb, p->k_stride_h, p->k_stride_s, varlen ? 0 : p->k_stride_b, "k")) return rc;
+    if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, rows_k, nb, p->v_stride_h, p->v_stride_s, varlen ? 0 : p->v_stride_b, "v")) return rc;
+    kp.dq = p->dq; kp.dk = p->dk; kp.dv = p->dv;
+    kp.dq_stride_b = p->dq_stride_b; kp.dq_stride_s = p->dq_stride_s; kp.dq_stride_h = p->dq_stride_h;
+    kp.dk_stride_b = p->dk_stride_b; kp.dk_stride_s = p->dk_stride_s; kp.dk_stride_h = p->dk_stride_h;
+    kp.dv_stride_b = p->dv_stride_b; kp.dv_stride_s = p->dv_stride_s; kp.dv_stride_h = p->dv_stride_h;
+    kp.lse = p->lse;
+    kp.delta = p->softmax_d;
+    kp.lse_stride_b = varlen ? 0 : (int64_t)p->num_heads * p->seqlen_q;
+    kp.lse_stride_h = varlen ? p->total_q : p->seqlen_q;
+    kp.cu_seqlens_q = varlen ? p->cu_seqlens_q : nullptr;
+    kp.cu_seqlens_k = varlen ? p->cu_seqlens_k : nullptr;
+    kp.alibi = p->alibi_slopes;
+    kp.alibi_stride_b = p->alibi_stride_b;
+    kp.seqlen_q = p->seqlen_q;
+    kp.seqlen_k = p->seqlen_k;
+    kp.num_heads = p->num_heads;
+    kp.heads_per_kv = p->num_heads / p->num_heads_k;
+    kp.scale = p->softmax_scale;
+    kp.scale_log2 = p->softmax_scale * fa::kLog2e;
+    kp.softcap = p->softcap;
+    kp.window_left = wl;
+    kp.window_right = wr;
+    kp.rp_dropout = 1.0f;
+    kp.drop_thr = 0xffffffffu;
+    const bool dropout = p->p_dropout > 0.f;
+    if (dropout) {
+        kp.rp_dropout = 1.0f / (1.0f - p->p_dropout);
+        kp.drop_thr = static_cast<uint32_t>((1.0f - p->p_dropout) * 4294967295.0f);
+        kp.drop_seed = p->dropout_seed;
+        kp.drop_offset = p->dropout_offset;
+    }
+    const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
+
+    // 1. delta = rowsum(dO * O)   (reference include/product.h; returned as softmax_d)
+    {
+        const int64_t rows = (int64_t)nb * rows_q * p->num_heads;
+        const int warps = 8;
+        const dim3 grid((unsigned)((rows + warps - 1) / warps));
+        const uint16_t* o = static_cast<const uint16_t*>(p->out);
+        const uint16_t* d = static_cast<const uint16_t*>(p->dout);
+        if (bf16)
+            fa::fa_bwd_dot_kernel<true><<<grid, warps * 32, 0, stream>>>(o, d, p->softmax_d, p->head_dim, rows, (int)rows_q, p->num_heads,
+                varlen ? 0 : p->o_stride_b, p->o_stride_s, p->o_stride_h, varlen ? 0 : p->do_stride_b, p->do_stride_s, p->do_stride_h,
+                kp.lse_stride_b, kp.lse_stride_h);
+        else
+            fa::fa_bwd_dot_kernel<false><<<grid, warps * 32, 0, stream>>>(o, d, p->softmax_d, p->head_dim, rows, (int)rows_q, p->num_heads,
+                varlen ? 0 : p->o_stride_b, p->o_stride_s, p->o_stride_h, varlen ? 0 : p->do_stride_b, p->do_stride_s, p->do_stride_h,
+                kp.lse_stride_b, kp.lse_stride_h);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "fa_bwd_dot_kernel launch");
+    }
+    // 2. dK / dV pass: one CTA per (128-key block, KV head, batch)
+    {
+        kp.num_blocks = (p->seqlen_k + 127) / 128;
+        kp.reverse = 0;
+        dim3 grid(kp.num_blocks, p->num_heads_k, p->batch);
+        if (int rc = launch_bwd<true>(kp, p->head_dim, bf16, feat, dropout, grid, stream)) return rc;
+    }
+    // 3. dQ pass: one CTA per (128-query block, head, batch)
+    {
+        kp.num_blocks = (p->seqlen_q + 127) / 128;
+        kp.reverse = wr >= 0 ? 1 : 0;
+        dim3 grid(kp.num_blocks, p->num_heads, p->batch);
+        if (int rc = launch_bwd<false>(kp, p->head_dim, bf16, feat, dropout, grid, stream)) return rc;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+FA_B200_API int fa_b200_bwd(const fa_b200_params_t* p, void* stream_v) { return bwd_common(p, stream_v, false); }
+FA_B200_API int fa_b200_varlen_bwd(const fa_b200_params_t* p, void* stream_v) { return bwd_common(p, stream_v, true); }
 
 }  // extern "C"

@@ -6,9 +6,8 @@ What differs is below the API: the reference permutes (B,S,H,D)->(B,H,S,D) and c
 `.contiguous()` three times on the way in and once on the way out (:36-53, :67); here the
 operator layer consumes strided views through TMA descriptors, so no tensor is copied.
 
-Forward only: the autograd.Function wrappers of the reference (:17-112, :157-269) exist there to
-route a backward pass that this build does not have; inputs that require grad
-are accepted but the result carries no grad_fn.
+The autograd.Function wrappers of the reference (:17-112, :157-269) are mirrored (FlashAttnFunc,
+FlashAttnVarlenFunc): same saved tensors, same gradient tuples, backed by the tcgen05 backward kernels.
 """
 from __future__ import annotations
 
@@ -37,6 +36,69 @@ def _pad8(x: torch.Tensor, pad: int) -> torch.Tensor:
 # ======================================================================================
 # DENSE ATTENTION (B, M, H, D)
 # ======================================================================================
+class FlashAttnFunc(torch.autograd.Function):
+    """Mirror of reference flash_attn_interface.py:17-112: same argument list, same saved state
+    (q, k, v, out, lse, rng_state + the scalar options), same gradient tuple. The [B,H,S,D] views handed to the
+    operator layer are permutes of the caller's tensors (consumed by stride; no transposing copies)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes,
+                deterministic, return_softmax, is_grad_enabled):
+        is_grad = is_grad_enabled and any(x.requires_grad for x in [q, k, v])
+        head_size_og = q.shape[-1]
+        pad = (8 - head_size_og % 8) % 8  # reference :44-49
+        q_, k_, v_ = (_pad8(maybe_contiguous(t), pad).permute(0, 2, 1, 3) for t in (q, k, v))
+        if softmax_scale is None:
+            softmax_scale = head_size_og ** -0.5  # from the unpadded dim, reference :55-56
+        window_left, window_right = window_size
+        out_, lse_, dmask_, rng_state = flash_attn_v100_cuda.fwd(
+            q_, k_, v_, None, alibi_slopes,
+            dropout_p, softmax_scale, causal,
+            window_left, window_right, softcap,
+            return_softmax, None,
+        )
+        out = out_[..., :head_size_og].permute(0, 2, 1, 3)
+        if not out.is_contiguous():
+            out = out.contiguous()
+        if is_grad:
+            ctx.save_for_backward(q_, k_, v_, out_, lse_, rng_state)
+            ctx.dropout_p = dropout_p
+            ctx.softmax_scale = softmax_scale
+            ctx.causal = causal
+            ctx.window_size = window_size
+            ctx.softcap = softcap
+            ctx.alibi_slopes = alibi_slopes
+            ctx.deterministic = deterministic
+            ctx.head_size_og = head_size_og
+            ctx.pad_size = pad
+        if return_softmax:
+            ctx.mark_non_differentiable(lse_, dmask_)
+            return out, lse_, dmask_
+        return out
+
+    @staticmethod
+    def backward(ctx, dout, *args):
+        q_, k_, v_, out_, lse_, rng_state = ctx.saved_tensors
+        head_size_og = ctx.head_size_og
+        dout_ = _pad8(maybe_contiguous(dout), ctx.pad_size).permute(0, 2, 1, 3)
+        window_left, window_right = ctx.window_size
+        # gradients are produced directly in the caller's (B, S, H, D) layout
+        dq = torch.empty((q_.shape[0], q_.shape[2], q_.shape[1], q_.shape[3]), dtype=q_.dtype, device=q_.device)
+        dk = torch.empty((k_.shape[0], k_.shape[2], k_.shape[1], k_.shape[3]), dtype=k_.dtype, device=k_.device)
+        dv = torch.empty_like(dk)
+        grads = flash_attn_v100_cuda.bwd(
+            dout_, q_, k_, v_, out_, lse_,
+            dq.permute(0, 2, 1, 3), dk.permute(0, 2, 1, 3), dv.permute(0, 2, 1, 3),
+            ctx.alibi_slopes,
+            ctx.dropout_p, ctx.softmax_scale, ctx.causal,
+            window_left, window_right,
+            ctx.softcap, ctx.deterministic, None, rng_state,
+        )
+        dq, dk, dv = (g[..., :head_size_og].permute(0, 2, 1, 3) for g in grads[:3])
+        dq, dk, dv = (g if g.is_contiguous() else g.contiguous() for g in (dq, dk, dv))
+        return dq, dk, dv, None, None, None, None, None, None, None, None, None
+
+
 def flash_attn_func(
     q: torch.Tensor,
     k: torch.Tensor,
@@ -52,25 +114,14 @@ def flash_attn_func(
 ):
     """Dense Flash Attention (B, M, H, D)"""
     if deterministic:
+        # the reference warns and clears the flag (:129-131); this build's backward is deterministic anyway
         warnings.warn("Forward is always deterministic. Deterministic backward is not supported.", RuntimeWarning)
         deterministic = False
     try:
-        head_size_og = q.shape[-1]
-        pad = (8 - head_size_og % 8) % 8  # reference :44-49
-        q_, k_, v_ = (_pad8(maybe_contiguous(t), pad).permute(0, 2, 1, 3) for t in (q, k, v))
-        if softmax_scale is None:
-            softmax_scale = head_size_og ** -0.5  # from the unpadded dim, reference :55-56
-        window_left, window_right = window_size
-        out_, lse_, dmask_, _rng = flash_attn_v100_cuda.fwd(
-            q_, k_, v_, None, alibi_slopes,
-            dropout_p, softmax_scale, causal,
-            window_left, window_right, softcap,
-            return_attn_probs, None,
+        return FlashAttnFunc.apply(
+            q, k, v, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes,
+            deterministic, return_attn_probs, torch.is_grad_enabled(),
         )
-        out = out_[..., :head_size_og].permute(0, 2, 1, 3)
-        if not out.is_contiguous():
-            out = out.contiguous()
-        return (out, lse_, dmask_) if return_attn_probs else out
     except Exception as e:
         print(f"[B200 FA2 DENSE FAILED] {type(e).__name__}: {e}")
         traceback.print_exc()
@@ -80,6 +131,72 @@ def flash_attn_func(
 # ======================================================================================
 # VARLEN ATTENTION (T, H, D)
 # ======================================================================================
+class FlashAttnVarlenFunc(torch.autograd.Function):
+    """Mirror of reference flash_attn_interface.py:157-269."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale,
+                causal, window_size, softcap, alibi_slopes, deterministic, return_attn_probs, block_table,
+                is_grad_enabled):
+        is_grad = is_grad_enabled and any(x.requires_grad for x in [q, k, v])
+        cu_seqlens_q = cu_seqlens_q.to(torch.int32).contiguous()
+        cu_seqlens_k = cu_seqlens_k.to(torch.int32).contiguous()
+        head_size_og = q.size(2)
+        pad = (8 - head_size_og % 8) % 8
+        q_, k_, v_ = (_pad8(maybe_contiguous(t), pad) for t in (q, k, v))
+        if softmax_scale is None:
+            softmax_scale = head_size_og ** -0.5
+        window_left, window_right = window_size
+        out_, lse, dmask, rng_state = flash_attn_v100_cuda.varlen_fwd(
+            q_, k_, v_, None, cu_seqlens_q, cu_seqlens_k,
+            None, None, block_table, alibi_slopes,
+            max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale,
+            False, causal, window_left, window_right, softcap,
+            return_attn_probs and dropout_p > 0.0, None, 0,
+        )
+        out = out_[..., :head_size_og]
+        if not out.is_contiguous():
+            out = out.contiguous()
+        if is_grad:
+            if block_table is not None:
+                raise RuntimeError("the backward has no paged-KV form (the reference's varlen_bwd takes no block_table)")
+            ctx.save_for_backward(q_, k_, v_, out_, lse, cu_seqlens_q, cu_seqlens_k, rng_state)
+            ctx.dropout_p = dropout_p
+            ctx.softmax_scale = softmax_scale
+            ctx.causal = causal
+            ctx.window_size = window_size
+            ctx.softcap = softcap
+            ctx.alibi_slopes = alibi_slopes
+            ctx.deterministic = deterministic
+            ctx.head_size_og = head_size_og
+            ctx.pad_size = pad
+            ctx.max_seqlen_q = max_seqlen_q
+            ctx.max_seqlen_k = max_seqlen_k
+        if return_attn_probs:
+            ctx.mark_non_differentiable(lse, dmask)
+            return out, lse, dmask
+        return out
+
+    @staticmethod
+    def backward(ctx, dout, *args):
+        q, k, v, out, lse, cu_seqlens_q, cu_seqlens_k, rng_state = ctx.saved_tensors
+        head_size_og = ctx.head_size_og
+        dout = _pad8(maybe_contiguous(dout), ctx.pad_size)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        window_left, window_right = ctx.window_size
+        grads = flash_attn_v100_cuda.varlen_bwd(
+            dout, q, k, v, out, lse,
+            dq, dk, dv, cu_seqlens_q, cu_seqlens_k,
+            ctx.alibi_slopes, ctx.max_seqlen_q, ctx.max_seqlen_k,
+            ctx.dropout_p, ctx.softmax_scale, False,
+            ctx.causal, window_left, window_right, ctx.softcap,
+            ctx.deterministic, None, rng_state,
+        )
+        dq, dk, dv = (g[..., :head_size_og] for g in grads[:3])
+        dq, dk, dv = (g if g.is_contiguous() else g.contiguous() for g in (dq, dk, dv))
+        return (dq, dk, dv) + (None,) * 14
+
+
 def flash_attn_varlen_func(
     q: torch.Tensor,
     k: torch.Tensor,
@@ -103,25 +220,11 @@ def flash_attn_varlen_func(
         warnings.warn("Forward is always deterministic. Deterministic backward is not supported.", RuntimeWarning)
         deterministic = False
     try:
-        cu_seqlens_q = cu_seqlens_q.to(torch.int32).contiguous()
-        cu_seqlens_k = cu_seqlens_k.to(torch.int32).contiguous()
-        head_size_og = q.size(2)
-        pad = (8 - head_size_og % 8) % 8
-        q_, k_, v_ = (_pad8(maybe_contiguous(t), pad) for t in (q, k, v))
-        if softmax_scale is None:
-            softmax_scale = head_size_og ** -0.5
-        window_left, window_right = window_size
-        out, lse, dmask, _rng = flash_attn_v100_cuda.varlen_fwd(
-            q_, k_, v_, None, cu_seqlens_q, cu_seqlens_k,
-            None, None, block_table, alibi_slopes,
-            max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale,
-            False, causal, window_left, window_right, softcap,
-            return_attn_probs and dropout_p > 0.0, None, 0,
+        return FlashAttnVarlenFunc.apply(
+            q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale,
+            causal, window_size, softcap, alibi_slopes, deterministic, return_attn_probs, block_table,
+            torch.is_grad_enabled(),
         )
-        out = out[..., :head_size_og]
-        if not out.is_contiguous():
-            out = out.contiguous()
-        return (out, lse, dmask) if return_attn_probs else out
     except Exception as e:
         print(f"[B200 FA2 VARLEN FAILED] {type(e).__name__}: {e}")
         traceback.print_exc()
@@ -185,6 +288,7 @@ flash_attn_varlen_gpu = flash_attn_varlen_func
 flash_attn_with_kvcache_gpu = flash_attn_with_kvcache
 
 __all__ = [
+    "FlashAttnFunc", "FlashAttnVarlenFunc",
     "flash_attn_func", "flash_attn_gpu",
     "flash_attn_varlen_func", "flash_attn_varlen_gpu",
     "flash_attn_with_kvcache", "flash_attn_with_kvcache_gpu",

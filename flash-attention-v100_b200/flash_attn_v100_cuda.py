@@ -13,7 +13,11 @@ callables, the same positional argument order and the same return lists
     fwd_kvcache(q, kcache, vcache, k, v, seqlens_k, rotary_cos, rotary_sin, cache_batch_idx,
         leftpad_k, block_table, alibi_slopes, out, softmax_scale, is_causal, window_left,
         window_right, softcap, is_rotary_interleaved, num_splits) -> [out, lse]
-    bwd(...), varlen_bwd(...)                              -> NotImplementedError (forward-only build)
+    bwd(dout, q, k, v, out, softmax_lse, dq, dk, dv, alibi_slopes, p_dropout, softmax_scale, is_causal,
+        window_left, window_right, softcap, deterministic, gen, rng_state) -> [dq, dk, dv, softmax_d]
+    varlen_bwd(dout, q, k, v, out, softmax_lse, dq, dk, dv, cu_seqlens_q, cu_seqlens_k, alibi_slopes,
+        max_seqlen_q, max_seqlen_k, p_dropout, softmax_scale, zero_tensors, is_causal, window_left,
+        window_right, softcap, deterministic, gen, rng_state)      -> [dq, dk, dv, softmax_d]
 
 Where the reference's wrappers (kernel/fused_mha_forward.cu:301-432, ..._varlen.cu:371-566,
 ..._kvcache.cu:416-652) validate with TORCH_CHECK and allocate outputs with ATen, this module
@@ -71,12 +75,17 @@ class FaB200Params(ctypes.Structure):
         ("workspace", _ptr), ("workspace_bytes", _i64),
         ("p_dropout", _f32), ("reserved3", _i32), ("dropout_seed", ctypes.c_uint64), ("dropout_offset", ctypes.c_uint64),
         ("dmask", _ptr),
+        ("dout", _ptr), ("dq", _ptr), ("dk", _ptr), ("dv", _ptr), ("softmax_d", _ptr),
+        ("do_stride_b", _i64), ("do_stride_s", _i64), ("do_stride_h", _i64),
+        ("dq_stride_b", _i64), ("dq_stride_s", _i64), ("dq_stride_h", _i64),
+        ("dk_stride_b", _i64), ("dk_stride_s", _i64), ("dk_stride_h", _i64),
+        ("dv_stride_b", _i64), ("dv_stride_s", _i64), ("dv_stride_h", _i64),
     ]
 
 
 EXPORTED_SYMBOLS = (
     "fa_b200_abi_version", "fa_b200_last_error", "fa_b200_workspace_bytes", "fa_b200_fwd",
-    "fa_b200_varlen_fwd", "fa_b200_kvcache_fwd", "fa_b200_launch_count",
+    "fa_b200_varlen_fwd", "fa_b200_kvcache_fwd", "fa_b200_launch_count", "fa_b200_bwd", "fa_b200_varlen_bwd",
 )
 
 _lib = None
@@ -97,12 +106,12 @@ def load_library() -> ctypes.CDLL:
     lib.fa_b200_launch_count.restype = ctypes.c_int64
     lib.fa_b200_workspace_bytes.restype = ctypes.c_int64
     lib.fa_b200_workspace_bytes.argtypes = [ctypes.POINTER(FaB200Params), ctypes.c_int]
-    for name in ("fa_b200_fwd", "fa_b200_varlen_fwd", "fa_b200_kvcache_fwd"):
+    for name in ("fa_b200_fwd", "fa_b200_varlen_fwd", "fa_b200_kvcache_fwd", "fa_b200_bwd", "fa_b200_varlen_bwd"):
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [ctypes.POINTER(FaB200Params), ctypes.c_void_p]
-    if lib.fa_b200_abi_version() != 2:
-        raise ImportError(f"libfa_b200.so ABI {lib.fa_b200_abi_version()} != 2")
+    if lib.fa_b200_abi_version() != 3:
+        raise ImportError(f"libfa_b200.so ABI {lib.fa_b200_abi_version()} != 3")
     _lib = lib
     return lib
 
@@ -472,12 +481,146 @@ def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_,
     return [out, lse]
 
 
-def bwd(*args, **kwargs):
-    raise NotImplementedError("backward is outside this build's scope (forward hot path only; SURVEY 8f rank 2)")
+def _bwd_dropout(p: FaB200Params, p_dropout: float, softcap: float, rng_state_) -> None:
+    _check(0.0 <= p_dropout < 1.0, "p_dropout must be in [0, 1)")
+    if softcap > 0.0:
+        _check(p_dropout == 0.0, "Softcapping does not support dropout")
+    if p_dropout > 0.0:  # reference kernel/fused_mha_backward.cu:659-666
+        _check(rng_state_ is not None and rng_state_.numel() == 2, "rng_state required when p_dropout > 0")
+        seed, offset = (int(x) & (2 ** 64 - 1) for x in rng_state_.tolist())
+        p.p_dropout, p.dropout_seed, p.dropout_offset = float(p_dropout), seed, offset
 
 
-def varlen_bwd(*args, **kwargs):
-    raise NotImplementedError("backward is outside this build's scope (forward hot path only; SURVEY 8f rank 2)")
+def _grad_out(given: Optional[torch.Tensor], like: torch.Tensor, name: str, ref: torch.Tensor) -> torch.Tensor:
+    """A gradient buffer the kernel can write: the caller's tensor if it is TMA/vector-store friendly."""
+    if given is not None:
+        _check(given.dtype == ref.dtype, f"{name} must have the same dtype as q")
+        _check(given.is_cuda, f"{name} must be on CUDA")
+        _check(given.stride(-1) == 1, f"{name} must have contiguous last dimension")
+        _check(given.shape == ref.shape, f"{name} shape must match {'q' if name == 'dq' else 'k'} shape")
+        if given.shape == like.shape and _aligned(given) is given:
+            return given
+    return torch.empty_like(like)
+
+
+def _finish_grad(buf: torch.Tensor, given: Optional[torch.Tensor], d: int) -> torch.Tensor:
+    res = buf[..., :d] if buf.shape[-1] != d else buf
+    if given is not None and given is not buf:
+        given.copy_(res)
+        return given
+    return res
+
+
+# ======================================================================================
+# dense backward:  replaces flash_attention_backward (reference kernel/fused_mha_backward.cu:590-721)
+# ======================================================================================
+def bwd(dout, q, k, v, out, softmax_lse, dq_, dk_, dv_, alibi_slopes_, p_dropout, softmax_scale, is_causal,
+        window_left, window_right, softcap, deterministic, gen_, rng_state_) -> List[torch.Tensor]:
+    """Tensors are [B, H, S, D] by strides, like `fwd`. Always deterministic (no atomics), so the
+    `deterministic` flag the reference rejects (:603) is accepted and has nothing to switch."""
+    _check(q.is_cuda and k.is_cuda and v.is_cuda, "Tensors q, k, v must be on CUDA")
+    _check(out.is_cuda and dout.is_cuda and softmax_lse.is_cuda, "out, dout, softmax_lse must be on CUDA")
+    dt = _dtype_code(q)
+    _check(k.dtype == q.dtype and v.dtype == q.dtype, "k/v must have the same dtype as q")
+    _check(out.dtype == q.dtype, "out must have the same dtype as q")
+    _check(dout.dtype == q.dtype, "dout must have the same dtype as q")
+    _check(softmax_lse.dtype == torch.float32, "softmax_lse must be fp32")
+    _check(q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1, "Last dim of q, k, v must be contiguous")
+    _check(out.stride(-1) == 1 and dout.stride(-1) == 1, "Last dim of out, dout must be contiguous")
+    B, H, M, D = q.shape
+    Hk, N = k.shape[1], k.shape[2]
+    _check(B > 0, "batch size must be positive")
+    _check(H % Hk == 0, "H_Q must be divisible by H_K for GQA/MQA")
+    _check(out.shape == q.shape and dout.shape == q.shape, "out and dout must have the shape of q")
+    _check(tuple(softmax_lse.shape) == (B, H, M), "softmax_lse must be [B, H_Q, M]")
+    Dp = _padded_dim(D)
+    p = FaB200Params()
+    _bwd_dropout(p, p_dropout, softcap, rng_state_)
+
+    softmax_d = torch.empty((B, H, M), dtype=torch.float32, device=q.device)
+    if M == 0 or N == 0:  # reference :696-701
+        grads = [t if t is not None else torch.empty_like(r) for t, r in ((dq_, q), (dk_, k), (dv_, v))]
+        for t in grads:
+            t.zero_()
+        softmax_d.zero_()
+        return grads + [softmax_d]
+
+    qp, kp, vp, op, dop = (_aligned(_pad_last(t, Dp)) for t in (q, k, v, out, dout))
+    lse = softmax_lse.contiguous()
+    dq, dk, dv = _grad_out(dq_, qp, "dq", q), _grad_out(dk_, kp, "dk", k), _grad_out(dv_, vp, "dv", k)
+    keep = [qp, kp, vp, op, dop, lse, dq, dk, dv, softmax_d]
+    p.dtype, p.device = dt, q.device.index if q.device.index is not None else torch.cuda.current_device()
+    p.batch, p.seqlen_q, p.seqlen_k, p.num_heads, p.num_heads_k, p.head_dim = B, M, N, H, Hk, Dp
+    p.q, p.k, p.v, p.out, p.lse = qp.data_ptr(), kp.data_ptr(), vp.data_ptr(), op.data_ptr(), lse.data_ptr()
+    p.dout, p.dq, p.dk, p.dv, p.softmax_d = dop.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), softmax_d.data_ptr()
+    for name, t in (("q", qp), ("k", kp), ("v", vp), ("o", op), ("do", dop), ("dq", dq), ("dk", dk), ("dv", dv)):
+        setattr(p, f"{name}_stride_b", t.stride(0))
+        setattr(p, f"{name}_stride_h", t.stride(1))
+        setattr(p, f"{name}_stride_s", t.stride(2))
+    _alibi(p, alibi_slopes_, B, H, keep)
+    p.softmax_scale, p.softcap = float(softmax_scale), float(softcap)
+    p.is_causal, p.window_left, p.window_right = int(bool(is_causal)), int(window_left), int(window_right)
+    _call("fa_b200_bwd", p, q.device)
+    return [_finish_grad(dq, dq_, D), _finish_grad(dk, dk_, D), _finish_grad(dv, dv_, D), softmax_d]
+
+
+# ======================================================================================
+# varlen backward:  replaces flash_attention_varlen_backward (reference kernel/fused_mha_backward_varlen.cu)
+# ======================================================================================
+def varlen_bwd(dout, q, k, v, out, softmax_lse, dq_, dk_, dv_, cu_seqlens_q, cu_seqlens_k, alibi_slopes_,
+               max_seqlen_q, max_seqlen_k, p_dropout, softmax_scale, zero_tensors, is_causal, window_left,
+               window_right, softcap, deterministic, gen_, rng_state_) -> List[torch.Tensor]:
+    """Packed layouts: q,out,dout,dq (T_q, H, D); k,v,dk,dv (T_k, H_K, D); softmax_lse / softmax_d [H, T_q]."""
+    _check(q.is_cuda and k.is_cuda and v.is_cuda, "Tensors q, k, v must be on CUDA")
+    _check(out.is_cuda and dout.is_cuda and softmax_lse.is_cuda, "out, dout, softmax_lse must be on CUDA")
+    dt = _dtype_code(q)
+    _check(k.dtype == q.dtype and v.dtype == q.dtype, "k/v must have the same dtype as q")
+    _check(out.dtype == q.dtype and dout.dtype == q.dtype, "out and dout must have the same dtype as q")
+    _check(softmax_lse.dtype == torch.float32, "softmax_lse must be fp32")
+    _check(q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1, "Last dim of q, k, v must be contiguous")
+    _check(out.stride(-1) == 1 and dout.stride(-1) == 1, "Last dim of out, dout must be contiguous")
+    for name, t in (("cu_seqlens_q", cu_seqlens_q), ("cu_seqlens_k", cu_seqlens_k)):
+        _check(t.dtype == torch.int32 and t.dim() == 1 and t.is_cuda and t.is_contiguous(),
+               f"{name} must be a contiguous 1-D int32 CUDA tensor")
+    T, H, D = q.shape
+    Tk, Hk = k.shape[0], k.shape[1]
+    B = cu_seqlens_q.numel() - 1
+    _check(B > 0, "batch size must be positive")
+    _check(cu_seqlens_k.numel() == B + 1, "cu_seqlens_k must have batch + 1 entries")
+    _check(H % Hk == 0, "H_Q must be divisible by H_K for GQA/MQA")
+    _check(out.shape == q.shape and dout.shape == q.shape, "out and dout must have the shape of q")
+    _check(tuple(softmax_lse.shape) == (H, T), "softmax_lse must be [H_Q, total_q]")
+    Dp = _padded_dim(D)
+    p = FaB200Params()
+    _bwd_dropout(p, p_dropout, softcap, rng_state_)
+
+    softmax_d = torch.zeros((H, T), dtype=torch.float32, device=q.device)
+    if T == 0 or Tk == 0 or max_seqlen_q == 0 or max_seqlen_k == 0:
+        grads = [t if t is not None else torch.empty_like(r) for t, r in ((dq_, q), (dk_, k), (dv_, v))]
+        for t in grads:
+            t.zero_()
+        return grads + [softmax_d]
+
+    qp, kp, vp, op, dop = (_aligned(_pad_last(t, Dp)) for t in (q, k, v, out, dout))
+    lse = softmax_lse.contiguous()
+    dq, dk, dv = _grad_out(dq_, qp, "dq", q), _grad_out(dk_, kp, "dk", k), _grad_out(dv_, vp, "dv", k)
+    if zero_tensors:
+        dq.zero_(), dk.zero_(), dv.zero_()
+    keep = [qp, kp, vp, op, dop, lse, dq, dk, dv, softmax_d, cu_seqlens_q, cu_seqlens_k]
+    p.dtype, p.device = dt, q.device.index if q.device.index is not None else torch.cuda.current_device()
+    p.batch, p.seqlen_q, p.seqlen_k, p.num_heads, p.num_heads_k, p.head_dim = B, int(max_seqlen_q), int(max_seqlen_k), H, Hk, Dp
+    p.total_q, p.total_k = T, Tk
+    p.q, p.k, p.v, p.out, p.lse = qp.data_ptr(), kp.data_ptr(), vp.data_ptr(), op.data_ptr(), lse.data_ptr()
+    p.dout, p.dq, p.dk, p.dv, p.softmax_d = dop.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), softmax_d.data_ptr()
+    for name, t in (("q", qp), ("k", kp), ("v", vp), ("o", op), ("do", dop), ("dq", dq), ("dk", dk), ("dv", dv)):
+        setattr(p, f"{name}_stride_s", t.stride(0))
+        setattr(p, f"{name}_stride_h", t.stride(1))
+    p.cu_seqlens_q, p.cu_seqlens_k = cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr()
+    _alibi(p, alibi_slopes_, B, H, keep)
+    p.softmax_scale, p.softcap = float(softmax_scale), float(softcap)
+    p.is_causal, p.window_left, p.window_right = int(bool(is_causal)), int(window_left), int(window_right)
+    _call("fa_b200_varlen_bwd", p, q.device)
+    return [_finish_grad(dq, dq_, D), _finish_grad(dk, dk_, D), _finish_grad(dv, dv_, D), softmax_d]
 
 
 # ======================================================================================

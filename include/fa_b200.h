@@ -12,6 +12,10 @@
  *                              (kernel/fused_mha_forward_varlen.cu:371-566)
  *   fa_b200_kvcache_fwd  <->  flash_attention_kvcache         include/mha.h:224-245
  *                              (kernel/fused_mha_forward_kvcache.cu:416-652)
+ *   fa_b200_bwd          <->  flash_attention_backward        include/mha.h:67-87
+ *                              (kernel/fused_mha_backward.cu:590-721)
+ *   fa_b200_varlen_bwd   <->  flash_attention_varlen_backward include/mha.h:170-195
+ *                              (kernel/fused_mha_backward_varlen.cu)
  *
  * The reference passes at::Tensor objects and allocates its outputs inside the wrapper; a C ABI
  * cannot, so here every tensor is a raw device pointer plus element strides, and the caller
@@ -32,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FA_B200_ABI_VERSION 2
+#define FA_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define FA_B200_API __attribute__((visibility("default")))
@@ -143,6 +147,20 @@ typedef struct fa_b200_params {
     uint64_t dropout_seed;
     uint64_t dropout_offset;
     void* dmask;           /* optional: +1.0 kept / -1.0 dropped in q's dtype; dense (B,H,Sq,Sk), varlen (total_q,H,max_seqlen_k) */
+
+    /* backward (fa_b200_bwd / fa_b200_varlen_bwd; reference include/mha.h:67-87, 170-195). Inputs: q, k, v,
+     * out, lse (from the forward), dout (layout of out). Outputs: dq, dk, dv (layouts of q, k, v; dk/dv have
+     * num_heads_k heads: the GQA group is summed inside the kernel) and softmax_d = rowsum(dout * out), fp32
+     * with the layout of lse. With p_dropout > 0 pass the forward's dropout_seed / dropout_offset (its rng_state). */
+    const void* dout;
+    void* dq;
+    void* dk;
+    void* dv;
+    float* softmax_d;
+    int64_t do_stride_b, do_stride_s, do_stride_h;
+    int64_t dq_stride_b, dq_stride_s, dq_stride_h;
+    int64_t dk_stride_b, dk_stride_s, dk_stride_h;
+    int64_t dv_stride_b, dv_stride_s, dv_stride_h;
 } fa_b200_params_t;
 
 /* kinds for fa_b200_workspace_bytes */
@@ -167,6 +185,12 @@ FA_B200_API int fa_b200_varlen_fwd(const fa_b200_params_t* params, void* cuda_st
 /* KV-cache forward (append + rotary + attention): replaces flash_attention_kvcache
  * (include/mha.h:224-245). Mutates the cache in place, like the reference. */
 FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* params, void* cuda_stream);
+
+/* Dense backward: replaces flash_attention_backward (reference include/mha.h:67-87). Deterministic. */
+FA_B200_API int fa_b200_bwd(const fa_b200_params_t* params, void* cuda_stream);
+
+/* Packed variable-length backward: replaces flash_attention_varlen_backward (include/mha.h:170-195). */
+FA_B200_API int fa_b200_varlen_bwd(const fa_b200_params_t* params, void* cuda_stream);
 
 /* Number of CUDA kernels this library has launched in this process (all threads). */
 FA_B200_API int64_t fa_b200_launch_count(void);

@@ -22,6 +22,11 @@ It restates, tile-free and in float64 (or float32 on request), what the referenc
       include/rotary.h:53-76;  paged addressing kernel/fused_mha_forward_varlen.cu:184-193
   * RoPE .................................... reference include/rotary.h:89-143,176-257
       y0 = fma(x0, c, -(x1*s)), y1 = fma(x0, s, x1*c) in fp32, rounded to the 16-bit dtype
+  * dropout ................................. reference include/softmax.h:96-125, include/philox.h
+      (Philox4x32-10; pinned on the Random123 known-answer vectors)
+  * backward ................................ reference include/softmax.h:205-406, include/product.h,
+      kernel/fused_mha_backward.cu (explicit formulas in attention_bwd_one; pinned on fixtures produced by
+      executing the reference's `ref_mha_backward`, test.py:36-61, and cross-checked against autograd)
 
 Documented positions where the reference is internally inconsistent (SURVEY 8a "quirks"): rows with no
 visible key give out = 0 and lse = -1e30 (the reference does this for wholly skipped tiles and the
@@ -147,6 +152,125 @@ def attention_one(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: floa
     out = torch.where(has_key.t().unsqueeze(-1), out, torch.zeros_like(out))
     lse = torch.where(has_key, m_safe + torch.log(l_safe), torch.full_like(m, NEG_SENTINEL))
     return out, lse
+
+
+def attention_bwd_one(q, k, v, dout, scale: float, wl: int, wr: int, slopes, softcap: float,
+                      dtype=torch.float64, keep: Optional[torch.Tensor] = None, p_dropout: float = 0.0):
+    """Backward of one sequence, restating the reference's formulas (not autograd):
+    q,dout:[Sq,H,D] k,v:[Sk,Hk,D] -> dq [Sq,H,D], dk,dv [Sk,Hk,D], delta [H,Sq].
+
+      delta_i = sum_d dO[i,d] O[i,d]                         reference include/product.h:9-96
+      P = exp(S - lse), P_drop = keep ? P/(1-p) : 0          include/softmax.h:270-291
+      dP = dO V^T                                            kernel/fused_mha_backward.cu:160-164 (dOV)
+      dS = (P_drop * dP - P * delta) * scale                 include/softmax.h:293-294
+      softcap: dS *= 1 - (S/softcap)^2, S the capped score   include/softmax.h:296-299
+      dQ = dS K;  dK = sum_group dS^T Q;  dV = sum_group P_drop^T dO   kernel/fused_mha_backward.cu:201-204, 351-470
+    ALiBi is a constant bias: it shapes P but has no gradient path of its own."""
+    Sq, H, D = q.shape
+    Sk, Hk, _ = k.shape
+    g = H // Hk
+    qf, kf, vf, dof = q.to(dtype), k.to(dtype), v.to(dtype), dout.to(dtype)
+    dq = torch.zeros((Sq, H, D), dtype=dtype)
+    dk = torch.zeros((Sk, Hk, D), dtype=dtype)
+    dv = torch.zeros((Sk, Hk, D), dtype=dtype)
+    delta = torch.zeros((H, Sq), dtype=dtype)
+    if Sk == 0 or Sq == 0:
+        return dq, dk, dv, delta
+    kr = kf.repeat_interleave(g, dim=1)
+    vr = vf.repeat_interleave(g, dim=1)
+    s = torch.einsum("qhd,khd->hqk", qf, kr) * scale
+    i = torch.arange(Sq).view(Sq, 1)
+    j = torch.arange(Sk).view(1, Sk)
+    off = Sk - Sq
+    if slopes is not None:
+        s = s - slopes.to(dtype).view(H, 1, 1) * (i + off - j).abs().to(dtype)
+    if softcap > 0.0:
+        s = softcap * torch.tanh(s / softcap)
+    masked = torch.zeros((Sq, Sk), dtype=torch.bool)
+    if wr >= 0:
+        masked |= j > i + off + wr
+    if wl >= 0:
+        masked |= j < i + off - wl
+    sm = s.masked_fill(masked.view(1, Sq, Sk), float("-inf"))
+    m = sm.max(dim=-1).values
+    has_key = torch.isfinite(m)
+    m_safe = torch.where(has_key, m, torch.zeros_like(m))
+    e = torch.exp(sm - m_safe.unsqueeze(-1))
+    l = torch.where(has_key, e.sum(dim=-1), torch.ones_like(m))
+    p = e / l.unsqueeze(-1)                       # == exp(S - lse); 0 on masked entries and key-less rows
+    p_drop = p if keep is None else p * keep.to(dtype).view(1, Sq, Sk) / (1.0 - p_dropout)
+    o = torch.einsum("hqk,khd->qhd", p_drop, vr)
+    delta = torch.einsum("qhd,qhd->hq", dof, o)
+    dp = torch.einsum("qhd,khd->hqk", dof, vr)
+    ds = (p_drop * dp - p * delta.unsqueeze(-1)) * scale
+    if softcap > 0.0:
+        ds = ds * (1.0 - (s / softcap) ** 2)
+    ds = ds.masked_fill(masked.view(1, Sq, Sk), 0.0)
+    dq = torch.einsum("hqk,khd->qhd", ds, kr)
+    dk = torch.einsum("hqk,qhd->khd", ds, qf).view(Sk, Hk, g, D).sum(dim=2)
+    dv = torch.einsum("hqk,qhd->khd", p_drop, dof).view(Sk, Hk, g, D).sum(dim=2)
+    return dq, dk, dv, delta
+
+
+def flash_attn_bwd_ref(dout, q, k, v, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
+                       alibi_slopes=None, dtype=torch.float64, dropout_p=0.0, rng_state=None):
+    """Dense backward. (B,S,H,D) layouts -> dq, dk, dv (same layouts), softmax_d (B,H,Sq)."""
+    dout, q, k, v = (t.detach().cpu() for t in (dout, q, k, v))
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    scale = D ** -0.5 if softmax_scale is None else softmax_scale
+    wl, wr = normalize_mask_args(Sq, Sk, causal, window_size, alibi_slopes is not None)
+    keep = None
+    if dropout_p > 0.0:
+        keep = dropout_keep_mask(dropout_p, int(rng_state[0]), int(rng_state[1]), 0, Sq, Sk, Sk)
+    res = [attention_bwd_one(q[b], k[b], v[b], dout[b], scale, wl, wr, _slopes_for(alibi_slopes, b), softcap,
+                             dtype, keep, dropout_p) for b in range(B)]
+    return tuple(torch.stack([r[n] for r in res]) for n in range(4))
+
+
+def flash_attn_varlen_bwd_ref(dout, q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k,
+                              softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
+                              alibi_slopes=None, dtype=torch.float64, dropout_p=0.0, rng_state=None):
+    """Packed backward. q,dout:(T,H,D) k,v:(Tk,Hk,D) -> dq, dk, dv, softmax_d (H,T)."""
+    dout, q, k, v = (t.detach().cpu() for t in (dout, q, k, v))
+    cu_q, cu_k = cu_seqlens_q.detach().cpu().long(), cu_seqlens_k.detach().cpu().long()
+    T, H, D = q.shape
+    B = cu_q.numel() - 1
+    scale = D ** -0.5 if softmax_scale is None else softmax_scale
+    causal_eff = causal and not (max_seqlen_q == 1 and alibi_slopes is None)
+    wl, wr = int(window_size[0]), int(window_size[1])
+    if wl >= max_seqlen_k:
+        wl = -1
+    if wr >= max_seqlen_k:
+        wr = -1
+    if causal_eff:
+        wr = 0
+    dq = torch.zeros((T, H, D), dtype=dtype)
+    dk = torch.zeros(tuple(k.shape), dtype=dtype)
+    dv = torch.zeros(tuple(k.shape), dtype=dtype)
+    delta = torch.zeros((H, T), dtype=dtype)
+    for b in range(B):
+        qs, qe, ks, ke = int(cu_q[b]), int(cu_q[b + 1]), int(cu_k[b]), int(cu_k[b + 1])
+        keep = None
+        if dropout_p > 0.0 and qe > qs and ke > ks:
+            keep = dropout_keep_mask(dropout_p, int(rng_state[0]), int(rng_state[1]), qs, qe - qs, ke - ks, int(max_seqlen_k))
+        a, b_, c, d = attention_bwd_one(q[qs:qe], k[ks:ke], v[ks:ke], dout[qs:qe], scale, wl, wr,
+                                        _slopes_for(alibi_slopes, b), softcap, dtype, keep, dropout_p)
+        dq[qs:qe], dk[ks:ke], dv[ks:ke], delta[:, qs:qe] = a, b_, c, d
+    return dq, dk, dv, delta
+
+
+def naive_lowp_attention_bwd(q, k, v, dout, scale, causal):
+    """The same-precision yardstick of reference test.py:36-61 (`ref_mha_backward`, upcast=False): autograd
+    through einsum / softmax / einsum in the tensors' own 16-bit dtype. (B,S,H,D), MHA only, top-left causal
+    as in test.py (it only uses Sq == Sk)."""
+    q, k, v = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k) * scale
+    if causal:
+        mask = torch.triu(torch.ones(s.shape[-2], s.shape[-1], device=s.device, dtype=torch.bool), diagonal=1)
+        s = s.masked_fill(mask, float("-inf"))
+    o = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, dim=-1), v)
+    return torch.autograd.grad(o, (q, k, v), dout)
 
 
 def _slopes_for(alibi_slopes: Optional[torch.Tensor], b: int) -> Optional[torch.Tensor]:

@@ -44,13 +44,37 @@ def kat():
     print("kat: out[0,:4] =", out[0, 0, :4])
 
 
-def load_ref_mha_forward():
+def load_ref_fn(name):
     src = open(os.path.join(REF, "test.py")).read()
     tree = ast.parse(src)
-    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "ref_mha_forward")
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
     ns = {"torch": torch}
     exec(compile(ast.Module(body=[fn], type_ignores=[]), "reference/test.py", "exec"), ns)
-    return ns["ref_mha_forward"]
+    return ns[name]
+
+
+def load_ref_mha_forward():
+    return load_ref_fn("ref_mha_forward")
+
+
+def mha_backward_fixtures():
+    """3. ref_mha_backward_*.npz -- the reference's backward oracle `ref_mha_backward` (test.py:36-61),
+    executed verbatim in fp32 (upcast=True) on seed-421 fp16 inputs and an fp16 dO drawn after them
+    (test.py:151-158)."""
+    ref_mha_backward = load_ref_fn("ref_mha_backward")
+    for (B, H, M, N, D) in [(1, 1, 64, 64, 64), (1, 2, 128, 128, 128), (1, 2, 256, 256, 64)]:
+        for causal in (False, True):
+            torch.manual_seed(421)
+            q = torch.randn(B, H, M, D, dtype=torch.float16)
+            k = torch.randn(B, H, N, D, dtype=torch.float16)
+            v = torch.randn(B, H, N, D, dtype=torch.float16)
+            do = torch.randn(B, H, M, D, dtype=torch.float16)
+            scale = 1.0 / (D ** 0.5)
+            dq, dk, dv = ref_mha_backward(q.float(), k.float(), v.float(), do.float(), scale=scale, causal=causal, upcast=True)
+            name = f"ref_mha_backward_B{B}_H{H}_M{M}_N{N}_D{D}_{'causal' if causal else 'full'}.npz"
+            np.savez_compressed(os.path.join(HERE, name), q=q.numpy(), k=k.numpy(), v=v.numpy(), do=do.numpy(),
+                                dq=dq.numpy(), dk=dk.numpy(), dv=dv.numpy(), scale=np.float32(scale), causal=np.int32(causal))
+            print(name, dq.abs().max().item(), dk.abs().max().item(), dv.abs().max().item())
 
 
 def mha_fixtures():
@@ -72,3 +96,4 @@ def mha_fixtures():
 if __name__ == "__main__":
     kat()
     mha_fixtures()
+    mha_backward_fixtures()

@@ -60,7 +60,7 @@ def test_library_exports_every_declared_symbol(fa_lib):
     assert sorted(declared) == sorted(op.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(fa_lib, name) is not None
-    assert fa_lib.fa_b200_abi_version() == 2
+    assert fa_lib.fa_b200_abi_version() == 3
     assert fa_lib.fa_b200_launch_count() == 0
 
 
@@ -106,10 +106,16 @@ def test_operator_layer_has_the_reference_surface():
         "window_right", "softcap", "return_softmax", "gen_"]
     assert len(inspect.signature(op.varlen_fwd).parameters) == 22
     assert len(inspect.signature(op.fwd_kvcache).parameters) == 20
-    with pytest.raises(NotImplementedError):
-        op.bwd()
-    with pytest.raises(NotImplementedError):
-        op.varlen_bwd()
+    # reference include/mha.h:67-87, 170-195
+    assert list(inspect.signature(op.bwd).parameters) == [
+        "dout", "q", "k", "v", "out", "softmax_lse", "dq_", "dk_", "dv_", "alibi_slopes_", "p_dropout", "softmax_scale",
+        "is_causal", "window_left", "window_right", "softcap", "deterministic", "gen_", "rng_state_"]
+    assert list(inspect.signature(op.varlen_bwd).parameters) == [
+        "dout", "q", "k", "v", "out", "softmax_lse", "dq_", "dk_", "dv_", "cu_seqlens_q", "cu_seqlens_k", "alibi_slopes_",
+        "max_seqlen_q", "max_seqlen_k", "p_dropout", "softmax_scale", "zero_tensors", "is_causal", "window_left",
+        "window_right", "softcap", "deterministic", "gen_", "rng_state_"]
+    assert issubclass(api.flash_attn_interface.FlashAttnFunc, __import__("torch").autograd.Function)
+    assert issubclass(api.flash_attn_interface.FlashAttnVarlenFunc, __import__("torch").autograd.Function)
     # reference flash_attn_v100/flash_attn_interface.py:115-127, 272-289, 323-343
     sig = inspect.signature(api.flash_attn_func)
     assert list(sig.parameters) == ["q", "k", "v", "dropout_p", "softmax_scale", "causal", "window_size", "softcap",
