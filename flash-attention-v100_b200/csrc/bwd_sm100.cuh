@@ -58,6 +58,7 @@ struct alignas(64) BwdKernelParams {
     int seqlen_k;  // dense Sk / var-len max_seqlen_k (also the dropout row length)
     int num_heads;
     int heads_per_kv;
+    int head_dim;      // real head dim (multiple of 8, <= D): TMA zero-fills columns [head_dim, D) of every tile
     float scale;
     float scale_log2;
     float softcap;
@@ -553,6 +554,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
             const bool wide_ok = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(dst) & 31) == 0);
 #pragma unroll
             for (int c = 0; c < HALF; c += 32) {
+                const int col = wg * HALF + c;  // columns [head_dim, D) are the tile's zero padding
+                if (col >= p.head_dim) break;
                 float o[32];
                 if (n_tiles > 0) {
                     tmem_ld_x32_wait(tmem_base + lane_off + tmem_col + wg * HALF + c, reinterpret_cast<uint32_t*>(o));
@@ -564,13 +567,14 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int e = 0; e < 32; e += 2) pk[e / 2] = pack2<BF16>(o[e] * mult, o[e + 1] * mult);
-                    if (wide_ok) {
+                    if (wide_ok && col + 32 <= p.head_dim) {
                         st_global_v8(dst + c, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
                         st_global_v8(dst + c + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
                     } else {
 #pragma unroll
                         for (int e = 0; e < 16; e += 4)
-                            *reinterpret_cast<uint4*>(dst + c + 2 * e) = make_uint4(pk[e], pk[e + 1], pk[e + 2], pk[e + 3]);
+                            if (col + 2 * e < p.head_dim)
+                                *reinterpret_cast<uint4*>(dst + c + 2 * e) = make_uint4(pk[e], pk[e + 1], pk[e + 2], pk[e + 3]);
                     }
                 }
             }

@@ -96,6 +96,10 @@ int check_device(int device) {
     return 0;
 }
 
+// Tile width the kernels are built for: the real head_dim (any multiple of 8) is rounded up to it and TMA
+// zero-fills the columns in between (the tensor maps carry the real head_dim as their innermost extent).
+int tile_dim(int head_dim) { return head_dim <= 64 ? 64 : 128; }
+
 template <int D, bool BF16, bool FEAT, bool DECODE = false, bool DROPOUT = false>
 int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
     using Cfg = fa::FwdConfig<D>;
@@ -115,8 +119,9 @@ int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) 
     return 0;
 }
 
-int launch_fwd(const fa::FwdKernelParams& kp, int head_dim, int dtype, bool feat, dim3 grid, cudaStream_t stream) {
+int launch_fwd(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, bool feat, dim3 grid, cudaStream_t stream) {
     const bool bf16 = dtype == FA_B200_DTYPE_BF16;
+    const int head_dim = tile_dim(real_head_dim);
     if (kp.drop_thr != 0xffffffffu) {  // dropout on: one variant per (D, dtype), with the score-modifier path compiled in
         if (head_dim == 128 && bf16) return launch_fwd_t<128, true, true, false, true>(kp, grid, stream);
         if (head_dim == 128) return launch_fwd_t<128, false, true, false, true>(kp, grid, stream);
@@ -138,8 +143,9 @@ int launch_fwd(const fa::FwdKernelParams& kp, int head_dim, int dtype, bool feat
 }
 
 // Decode path: packed-GQA split-KV launch + combine.
-int launch_decode(const fa::FwdKernelParams& kp, int head_dim, int dtype, dim3 grid, cudaStream_t stream) {
+int launch_decode(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, dim3 grid, cudaStream_t stream) {
     const bool bf16 = dtype == FA_B200_DTYPE_BF16;
+    const int head_dim = tile_dim(real_head_dim);
     if (head_dim == 128 && bf16) return launch_fwd_t<128, true, false, true>(kp, grid, stream);
     if (head_dim == 128 && !bf16) return launch_fwd_t<128, false, false, true>(kp, grid, stream);
     if (head_dim == 64 && bf16) return launch_fwd_t<64, true, false, true>(kp, grid, stream);
@@ -155,9 +161,9 @@ int launch_combine(const fa::FwdKernelParams& kp, const fa_b200_params_t* p, cud
     const bool bf16 = p->dtype == FA_B200_DTYPE_BF16;
 #define FA_COMBINE(DD, BB)                                                                                   \
     fa::fa_combine_kernel<DD, BB><<<grid, warps * 32, 0, stream>>>(kp.o_partial, kp.lse_partial, out, p->lse, \
-        kp.num_splits, p->batch, p->num_heads, p->seqlen_q, p->o_stride_b, p->o_stride_s, p->o_stride_h)
-    if (p->head_dim == 128 && bf16) FA_COMBINE(128, true);
-    else if (p->head_dim == 128) FA_COMBINE(128, false);
+        kp.num_splits, p->batch, p->num_heads, p->seqlen_q, p->o_stride_b, p->o_stride_s, p->o_stride_h, p->head_dim)
+    if (tile_dim(p->head_dim) == 128 && bf16) FA_COMBINE(128, true);
+    else if (tile_dim(p->head_dim) == 128) FA_COMBINE(128, false);
     else if (bf16) FA_COMBINE(64, true);
     else FA_COMBINE(64, false);
 #undef FA_COMBINE
@@ -201,7 +207,7 @@ int64_t decode_workspace_bytes(const fa_b200_params_t* p) {
     const int s = decode_num_splits(p);
     if (s <= 1) return 0;
     const int64_t rows = (int64_t)s * p->batch * p->num_heads * p->seqlen_q;
-    return ((rows * p->head_dim * 4 + 255) & ~(int64_t)255) + ((rows * 4 + 255) & ~(int64_t)255);
+    return ((rows * tile_dim(p->head_dim) * 4 + 255) & ~(int64_t)255) + ((rows * 4 + 255) & ~(int64_t)255);
 }
 
 // Scheduler state for the persistent kernel: one pair of ints (next work id, CTAs done) per launch.
@@ -271,9 +277,9 @@ int check_common(const fa_b200_params_t* p) {
     CHECK_ARG(p->num_heads > 0 && p->num_heads_k > 0, "head counts must be positive");
     CHECK_ARG(p->num_heads % p->num_heads_k == 0, "H_Q must be divisible by H_K for GQA/MQA");
     CHECK_ARG(p->head_dim % 8 == 0, "head dimension must be multiple of 8");
-    CHECK_ARG(p->head_dim <= 256, "head dimension must be <= 256");
-    if (p->head_dim != 64 && p->head_dim != 128)
-        return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (64 and 128 are; the Python layer pads smaller dims)", p->head_dim);
+    CHECK_ARG(p->head_dim > 0 && p->head_dim <= 256, "head dimension must be <= 256");
+    if (p->head_dim > 128)
+        return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (any multiple of 8 up to 128 is)", p->head_dim);
     CHECK_ARG(p->q && p->k && p->v && p->out && p->lse, "q, k, v, out and lse must be non-NULL");
     CHECK_ARG(p->softcap >= 0.f, "softcap must be >= 0");
     CHECK_ARG((reinterpret_cast<uintptr_t>(p->out) & 15) == 0 && p->o_stride_b % 8 == 0 && p->o_stride_s % 8 == 0 &&
@@ -293,6 +299,7 @@ void fill_common(fa::FwdKernelParams& kp, const fa_b200_params_t* p, bool causal
     kp.alibi_stride_b = p->alibi_stride_b;
     kp.num_heads = p->num_heads;
     kp.heads_per_kv = p->num_heads / p->num_heads_k;
+    kp.head_dim = p->head_dim;
     kp.scale = p->softmax_scale;
     kp.scale_log2 = p->softmax_scale * fa::kLog2e;
     kp.softcap = p->softcap;
@@ -585,7 +592,7 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
         kp.num_splits = decode_num_splits(p);
         if (kp.num_splits > 1) {
             const int64_t prow = (int64_t)kp.num_splits * p->batch * p->num_heads * p->seqlen_q;
-            const int64_t obytes = (prow * p->head_dim * 4 + 255) & ~(int64_t)255;
+            const int64_t obytes = (prow * tile_dim(p->head_dim) * 4 + 255) & ~(int64_t)255;
             const int64_t lbytes = (prow * 4 + 255) & ~(int64_t)255;
             CHECK_ARG(ws != nullptr && ws_left >= obytes + lbytes, "workspace too small for %d KV splits (see fa_b200_workspace_bytes)", kp.num_splits);
             kp.o_partial = reinterpret_cast<float*>(ws);
@@ -627,7 +634,8 @@ int launch_bwd_t(const fa::BwdKernelParams& kp, dim3 grid, cudaStream_t stream) 
 }
 
 template <bool KV_STAT>
-int launch_bwd(const fa::BwdKernelParams& kp, int head_dim, bool bf16, bool feat, bool dropout, dim3 grid, cudaStream_t stream) {
+int launch_bwd(const fa::BwdKernelParams& kp, int real_head_dim, bool bf16, bool feat, bool dropout, dim3 grid, cudaStream_t stream) {
+    const int head_dim = tile_dim(real_head_dim);
     // dropout variants are built with the score-modifier path compiled in (one variant per D and dtype)
 #define FA_BCASE(DD, BB)                                                                                       \
     if (head_dim == DD && bf16 == BB) {                                                                        \
@@ -704,6 +712,7 @@ int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
     kp.seqlen_k = p->seqlen_k;
     kp.num_heads = p->num_heads;
     kp.heads_per_kv = p->num_heads / p->num_heads_k;
+    kp.head_dim = p->head_dim;
     kp.scale = p->softmax_scale;
     kp.scale_log2 = p->softmax_scale * fa::kLog2e;
     kp.softcap = p->softcap;

@@ -20,6 +20,11 @@
 //
 // TMEM map (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D);
 // P_s aliases columns [64,128) of S_s (128 x 128 16-bit values = 64 columns).
+//
+// head_dim 256 ("split-D"): an O accumulator of 256 columns per query tile leaves no room for two stages, so
+// the two stages work on the SAME 128 query rows and each owns one 128-column half of O (stage s multiplies P
+// by V[:, 128 s .. 128 s + 128)). Both compute S = Q K^T over all 256 dims and the same softmax; Q, K and V are
+// loaded once per tile and shared. A work item is then one 128-row query block, and the TMEM map is unchanged.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -56,6 +61,7 @@ struct alignas(64) FwdKernelParams {
     int seqlen_k_add;  // rows appended to the cache before this call (kvcache)
     int num_heads;
     int heads_per_kv;
+    int head_dim;      // real head dim (multiple of 8, <= D): TMA zero-fills columns [head_dim, D) of every tile
     float scale;
     float scale_log2;
     float softcap;
@@ -150,8 +156,11 @@ struct FwdConfig {
     static constexpr int kBlockN = 128;
     static constexpr int kTileBytes = kBlockN * D * 2;
     static constexpr int kHalfBytes = kBlockN * 128;  // one 64-column (128-byte) swizzle block
-    static constexpr int kKvStages = (D == 128) ? 4 : 6;
-    static constexpr int kSmemQ = 2 * kTileBytes;
+    static constexpr bool kSplitD = (D == 256);            // see "split-D" in the header comment
+    static constexpr int kDO = kSplitD ? 128 : D;          // columns of one stage's O accumulator
+    static constexpr int kItemRows = kSplitD ? kBlockM : 2 * kBlockM;  // query rows of one work item
+    static constexpr int kKvStages = (D == 256) ? 2 : (D == 128) ? 4 : 6;
+    static constexpr int kSmemQ = kSplitD ? kTileBytes : 2 * kTileBytes;
     static constexpr int kSmemKV = kKvStages * kTileBytes;
     static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1;
     static constexpr int kOffBars = kSmemQ + kSmemKV;
@@ -162,7 +171,7 @@ struct FwdConfig {
     static constexpr int kOffSched = kOffRowMax + 2 * 2 * 128 * 4;   // int[2] work ids
     static constexpr int kSmemUsed = kOffSched + 16;
     static constexpr int kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
-    static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + D;
+    static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + kDO;
     static constexpr int kTmemPOff = 64;
 };
 
@@ -218,9 +227,10 @@ struct WorkGeom {
     bool skip;           // nothing to do and nothing to write (query block past the sequence end)
 };
 
-template <bool DECODE>
+template <bool DECODE, bool SPLIT = false>
 FA_DEVICE WorkGeom work_geom(const FwdKernelParams& p, int work_id) {
     constexpr int BM = 128, BN = 128;
+    constexpr int ROWS = SPLIT ? BM : 2 * BM;  // query rows per work item
     WorkGeom w;
     const int G = DECODE ? p.gqa_pack : 1;
     int m_block = 0;
@@ -244,9 +254,9 @@ FA_DEVICE WorkGeom work_geom(const FwdKernelParams& p, int work_id) {
         w.kv_head = w.head / p.heads_per_kv;
     }
     w.g = load_geom(p, w.batch);
-    w.m0 = m_block * (2 * BM);
+    w.m0 = m_block * ROWS;
     w.skip = w.m0 >= w.g.seqlen_q;  // over-provisioned varlen grid
-    w.m_end = DECODE ? w.g.seqlen_q : min(w.m0 + 2 * BM, w.g.seqlen_q);
+    w.m_end = DECODE ? w.g.seqlen_q : min(w.m0 + ROWS, w.g.seqlen_q);
     w.off = w.g.seqlen_k - w.g.seqlen_q;
     w.o_b = p.cu_seqlens_q ? 0 : w.batch;
     int n_max = (w.g.seqlen_k + BN - 1) / BN;
@@ -273,10 +283,10 @@ FA_DEVICE WorkGeom work_geom(const FwdKernelParams& p, int work_id) {
     // causal diagonal or wholly left of its window are skipped for that stage.
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-        const int r0 = w.m0 + s * BM;
+        const int r0 = w.m0 + (SPLIT ? 0 : s * BM);
         int hi_n = n_max, lo_n = n_min;
         if (DECODE) {
-            if (s == 1) hi_n = lo_n = n_min;  // single tile of packed rows: stage 1 is idle
+            if (s == 1 && !SPLIT) hi_n = lo_n = n_min;  // single tile of packed rows: stage 1 is idle
         } else if (r0 >= w.g.seqlen_q) {
             hi_n = lo_n = n_min;  // no valid row in this stage
         } else {
@@ -309,6 +319,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     using Cfg = FwdConfig<D>;
     constexpr int BM = Cfg::kBlockM, BN = Cfg::kBlockN;
     constexpr int KV = Cfg::kKvStages;
+    constexpr bool SPLIT = Cfg::kSplitD;
+    constexpr int DO = Cfg::kDO;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_raw_u32 = smem_u32(smem_raw);
@@ -413,7 +425,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 // Query blocks past the end of their sequence (the var-len grid is sized for the longest
                 // sequence) have nothing to compute or write: drop them here instead of sending every warp
                 // through a scheduler hand-shake for them.
-                while (id < total_work && work_geom<DECODE>(p, id).skip) id = fetch();
+                while (id < total_work && work_geom<DECODE, SPLIT>(p, id).skip) id = fetch();
                 // publish the k-th work id (slot k&1 is free once everyone consumed item k-2)
                 if (k >= 2) mbar_wait(bar_sched_empty(k & 1), ((k >> 1) - 1) & 1);
                 if (lane == 0) {
@@ -425,7 +437,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 id = total_work;
             }
             if (id >= total_work) break;
-            const WorkGeom w = work_geom<DECODE>(p, id);
+            const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
             int next_id = total_work;
             if constexpr (!DECODE) next_id = fetch();  // early: the atomic's latency hides behind the loads
             if (w.n_tiles > 0) {
@@ -456,7 +468,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 // DECODE: tm_q's box is (64, G, 128/G, 1), so one load brings the G heads of 128/G positions
                 if (lane == 0) load_tile(&p.tm_q, sQ, bar_q_full(0), w.head, w.g.q_off + w.m0, w.g.q_b);
                 produce(&p.tm_k, w.n_max - 1);
-                if (!DECODE && lane == 0)
+                if (!DECODE && !SPLIT && lane == 0)
                     load_tile(&p.tm_q, sQ + Cfg::kTileBytes, bar_q_full(1), w.head, w.g.q_off + w.m0 + BM, w.g.q_b);
                 produce(&p.tm_v, w.n_max - 1);
                 for (int it = 1; it < w.n_tiles; ++it) {
@@ -481,7 +493,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         // ============================================================ MMA issuer
         reg_dec<48>();
         constexpr uint32_t idesc_qk = umma_idesc_f16(BF16, BM, BN, false, false);
-        constexpr uint32_t idesc_pv = umma_idesc_f16(BF16, BM, D, false, true);
+        constexpr uint32_t idesc_pv = umma_idesc_f16(BF16, BM, DO, false, true);
         const uint32_t tS[2] = {tmem_base + Cfg::kTmemS0, tmem_base + Cfg::kTmemS1};
         const uint32_t tO[2] = {tmem_base + Cfg::kTmemO0, tmem_base + Cfg::kTmemO1};
         // Descriptor words (ptx_sm100.cuh): lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version | swizzle.
@@ -493,9 +505,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         auto lo_addr = [](uint32_t saddr) { return (saddr & 0x3FFFFu) >> 4; };
         // The whole warp stays convergent; each issue block elects one lane (umma_issue_gen.cuh).
         auto issue_qk = [&](int s, uint32_t k_smem) {
-            const uint32_t a_lo = lo_addr(sQ + s * Cfg::kTileBytes) | kLoKmajor;
+            const uint32_t a_lo = lo_addr(sQ + (SPLIT ? 0 : s) * Cfg::kTileBytes) | kLoKmajor;
             const uint32_t b_lo = lo_addr(k_smem) | kLoKmajor;
-            if constexpr (D == 128) umma_issue_qk_d128(tS[s], a_lo, b_lo, kDescHi, kDescHi, idesc_qk);
+            if constexpr (D == 256) umma_issue_qk_d256(tS[s], a_lo, b_lo, kDescHi, kDescHi, idesc_qk);
+            else if constexpr (D == 128) umma_issue_qk_d128(tS[s], a_lo, b_lo, kDescHi, kDescHi, idesc_qk);
             else umma_issue_qk_d64(tS[s], a_lo, b_lo, kDescHi, kDescHi, idesc_qk);
         };
         auto slot_addr = [&](int r) { return sKV + (r % KV) * Cfg::kTileBytes; };
@@ -508,7 +521,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         for (int k = 0;; ++k) {
             const int id = get_work(k);
             if (id >= total_work) break;
-            const WorkGeom w = work_geom<DECODE>(p, id);
+            const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
             if (w.n_tiles <= 0) continue;
             mbar_wait(bar_q_full(0), ka & 1);
             // Issue order per iteration: PV0(it-1) QK0(it) PV1(it-1) QK1(it). tcgen05 ops execute in issue
@@ -518,7 +531,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 if (it > 0) wait_full(ring + 2 * it - 1);
                 if (it == 1 && w.ragged_tail) mbar_wait(bar_vfix, kfix & 1);  // V rows past seqlen_k are zero now
                 if (it < w.n_tiles) wait_full(ring + 2 * it);
-                if (!DECODE && it == 0) mbar_wait(bar_q_full(1), ka & 1);
+                if (!DECODE && !SPLIT && it == 0) mbar_wait(bar_q_full(1), ka & 1);
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     const bool do_pv = it > 0 && (it - 1) >= w.it_lo[s] && (it - 1) < w.it_hi[s];
@@ -527,7 +540,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         const int j = it - 1 - w.it_lo[s];
                         const uint32_t ph = (steps[s] + j) & 1;
                         const uint32_t tP = tS[s] + Cfg::kTmemPOff;
-                        const uint32_t v_lo = lo_addr(slot_addr(ring + 2 * it - 1)) | kLoVmn;
+                        // split-D: stage s multiplies by its own 128-column half of V (two swizzle blocks further)
+                        const uint32_t v_lo = lo_addr(slot_addr(ring + 2 * it - 1) + (SPLIT ? s * 2 * Cfg::kHalfBytes : 0)) | kLoVmn;
                         // P_s(j) written, O_s rescaled; for j == 0 this also means the correction warps
                         // finished reading O_s of the previous item (their arrival comes after that epilogue)
                         mbar_wait(bar_p_full(s), ph);
@@ -576,11 +590,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         for (int k = 0;; ++k) {
             const int id = get_work(k);
             if (id >= total_work) break;
-            const WorkGeom w = work_geom<DECODE>(p, id);
+            const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
             const int my_lo = s == 0 ? w.it_lo[0] : w.it_lo[1];
             const int my_n = (s == 0 ? w.it_hi[0] : w.it_hi[1]) - my_lo;
             if (my_n <= 0) continue;
-            const int i_glob = DECODE ? row / G : w.m0 + s * BM + row;  // query position inside the sequence
+            const int i_glob = DECODE ? row / G : w.m0 + (SPLIT ? 0 : s * BM) + row;  // query position inside the sequence
 
             // visible key range of this row: [col_lo, col_hi)
             int col_hi = w.g.seqlen_k;
@@ -603,7 +617,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             uint16_t* dm_row = nullptr;
             if constexpr (DROPOUT) {
                 drop_row_idx = (uint64_t)(w.g.q_off + i_glob) * (uint64_t)p.seqlen_k;
-                if (p.dmask && i_glob < w.g.seqlen_q)
+                if (p.dmask && i_glob < w.g.seqlen_q && !(SPLIT && s == 1))  // split-D: both stages hold the same mask
                     dm_row = p.dmask + w.o_b * p.dmask_stride_b + w.head * p.dmask_stride_h +
                              (int64_t)(w.g.q_off + i_glob) * p.dmask_stride_row;
             }
@@ -760,7 +774,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         for (int k = 0;; ++k) {
             const int id = get_work(k);
             if (id >= total_work) break;
-            const WorkGeom w = work_geom<DECODE>(p, id);
+            const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
             if (w.skip) continue;
             if (w.n_tiles <= 0) {
                 // No visible key for any row of this block: out = 0, lse = sentinel (reference
@@ -774,8 +788,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                                           w.g.seqlen_q + r / G] = -INFINITY;
                     continue;
                 }
-                for (int idx = t; idx < rows * (D / 8); idx += 128) {
-                    const int r = idx / (D / 8), c = idx % (D / 8);
+                const int hd8 = p.head_dim / 8;
+                for (int idx = t; idx < rows * hd8; idx += 128) {
+                    const int r = idx / hd8, c = idx % hd8;
                     uint16_t* dst = outp + w.o_b * p.o_stride_b + (int64_t)(w.g.q_off + w.m0 + r / G) * p.o_stride_s +
                                     (w.head + r % G) * p.o_stride_h + c * 8;
                     *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
@@ -795,7 +810,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     if (j > 0 && __any_sync(0xffffffffu, sc != 1.0f)) {
                         tc_fence_after();
 #pragma unroll
-                        for (int c = 0; c < D / 32; ++c) {
+                        for (int c = 0; c < DO / 32; ++c) {
                             float o[32];
                             tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
 #pragma unroll
@@ -812,18 +827,22 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             // epilogue: out = O / l, lse = m + ln(l)   (reference kernel/fused_mha_forward.cu:215-223)
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                if (DECODE && s == 1) continue;  // packed-row mode has a single tile
-                const int i_glob = DECODE ? row / G : w.m0 + s * BM + row;
+                if (DECODE && !SPLIT && s == 1) continue;  // packed-row mode has a single tile
+                const int i_glob = DECODE ? row / G : w.m0 + (SPLIT ? 0 : s * BM) + row;
                 const int h_row = DECODE ? w.head + row % G : w.head;
                 const bool valid = i_glob < w.g.seqlen_q;
+                constexpr int kColStep = SPLIT ? DO : 0;  // split-D: stage s owns output columns [s*128, s*128+128)
+                const int col0 = s * kColStep;
+                const bool own_lse = !(SPLIT && s == 1);
                 uint16_t* dst = outp + w.o_b * p.o_stride_b + (int64_t)(w.g.q_off + i_glob) * p.o_stride_s +
-                                h_row * p.o_stride_h;
+                                h_row * p.o_stride_h + col0;
                 float* lse_dst = p.lse + w.o_b * p.lse_stride_b + h_row * p.lse_stride_h + w.g.q_off + i_glob;
                 if (w.it_hi[s] <= w.it_lo[s]) {  // this stage saw no KV tile: no key is visible to its rows
                     if (valid) {
 #pragma unroll
-                        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
-                        *lse_dst = kNegSentinel;
+                        for (int c = 0; c < DO; c += 8)
+                            if (col0 + c < p.head_dim) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
+                        if (own_lse) *lse_dst = kNegSentinel;
                     }
                     continue;
                 }
@@ -840,37 +859,39 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     // split-KV partial: normalised fp32 O and this split's LSE; fa_combine_kernel merges them
                     const int64_t prow = (((int64_t)w.split * num_batch + w.batch) * p.num_heads + h_row) * w.g.seqlen_q + i_glob;
 #pragma unroll
-                    for (int c = 0; c < D / 32; ++c) {
+                    for (int c = 0; c < DO / 32; ++c) {
                         float o[32];
                         tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
                         if (valid) {
 #pragma unroll
                             for (int e = 0; e < 32; e += 4)
-                                *reinterpret_cast<float4*>(p.o_partial + prow * D + c * 32 + e) =
+                                *reinterpret_cast<float4*>(p.o_partial + prow * D + col0 + c * 32 + e) =
                                     make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
                         }
                     }
-                    if (valid) p.lse_partial[prow] = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : -INFINITY;
+                    if (valid && own_lse) p.lse_partial[prow] = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : -INFINITY;
                 } else {
 #pragma unroll
-                    for (int c = 0; c < D / 32; ++c) {
+                    for (int c = 0; c < DO / 32; ++c) {
+                        if (col0 + c * 32 >= p.head_dim) break;  // columns [head_dim, D) are the tile's zero padding
                         float o[32];
                         tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
                         if (valid) {
                             uint32_t pk[16];
 #pragma unroll
                             for (int e = 0; e < 32; e += 2) pk[e / 2] = pack2<BF16>(o[e] * inv, o[e + 1] * inv);
-                            if (wide_ok) {  // 2 x 32 B per 32 columns instead of 4 x 16 B
+                            if (wide_ok && col0 + c * 32 + 32 <= p.head_dim) {  // 2 x 32 B per 32 columns instead of 4 x 16 B
                                 st_global_v8(dst + c * 32, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
                                 st_global_v8(dst + c * 32 + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
                             } else {
 #pragma unroll
                                 for (int e = 0; e < 16; e += 4)
-                                    *reinterpret_cast<uint4*>(dst + c * 32 + 2 * e) = make_uint4(pk[e], pk[e + 1], pk[e + 2], pk[e + 3]);
+                                    if (col0 + c * 32 + 2 * e < p.head_dim)
+                                        *reinterpret_cast<uint4*>(dst + c * 32 + 2 * e) = make_uint4(pk[e], pk[e + 1], pk[e + 2], pk[e + 3]);
                             }
                         }
                     }
-                    if (valid) *lse_dst = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : kNegSentinel;
+                    if (valid && own_lse) *lse_dst = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : kNegSentinel;
                 }
                 steps[s] += w.it_hi[s] - w.it_lo[s];
                 ++items[s];
@@ -888,7 +909,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         for (int k = 0;; ++k) {
             const int id = get_work(k);
             if (id >= total_work) break;
-            const WorkGeom w = work_geom<DECODE>(p, id);
+            const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
             if (w.n_tiles <= 0) continue;
             if (w.ragged_tail) {
                 const int v_entry = ring + 1;
@@ -922,7 +943,7 @@ template <int D, bool BF16>
 __global__ void fa_combine_kernel(const float* __restrict__ o_partial, const float* __restrict__ lse_partial,
                                   uint16_t* __restrict__ out, float* __restrict__ lse, int num_splits, int batch,
                                   int heads, int seqlen_q, int64_t o_stride_b, int64_t o_stride_s,
-                                  int64_t o_stride_h) {
+                                  int64_t o_stride_h, int head_dim) {
     const int lane = threadIdx.x & 31;
     const int64_t rows = (int64_t)batch * heads * seqlen_q;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -949,7 +970,8 @@ __global__ void fa_combine_kernel(const float* __restrict__ o_partial, const flo
     const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
     uint16_t* dst = out + b * o_stride_b + (int64_t)pos * o_stride_s + h * o_stride_h + lane * E;
 #pragma unroll
-    for (int e = 0; e < E; e += 2) *reinterpret_cast<uint32_t*>(dst + e) = pack2<BF16>(acc[e] * inv, acc[e + 1] * inv);
+    for (int e = 0; e < E; e += 2)
+        if (lane * E + e < head_dim) *reinterpret_cast<uint32_t*>(dst + e) = pack2<BF16>(acc[e] * inv, acc[e + 1] * inv);
     if (lane == 0) lse[((int64_t)b * heads + h) * seqlen_q + pos] = wsum > 0.f ? mx + __logf(wsum) : kNegSentinel;
 }
 

@@ -146,13 +146,13 @@ def _call(fn_name: str, params: FaB200Params, device: torch.device) -> None:
 
 
 def _padded_dim(d: int) -> int:
+    """Head dims the C layer takes: any multiple of 8 (the reference's own check, kernel/fused_mha_forward.cu:335);
+    the kernels' tiles are 64 / 128 wide and TMA zero-fills the columns past `d`, so nothing is padded here."""
     _check(d <= 256, "head dimension must be <= 256")
     _check(d % 8 == 0, "head dimension must be multiple of 8")
-    if d <= 64:
-        return 64
-    if d <= 128:
-        return 128
-    raise NotImplementedError(f"head_dim {d} > 128 is not built yet (SURVEY 8f rank 3)")
+    if d > 128:
+        raise NotImplementedError(f"head_dim {d} > 128 is not built yet (SURVEY 8f rank 3)")
+    return d
 
 
 def _pad_last(x: Optional[torch.Tensor], d_to: int) -> Optional[torch.Tensor]:
@@ -375,7 +375,7 @@ def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_,
     _check(q.stride(-1) == 1 and kcache.stride(-1) == 1 and vcache.stride(-1) == 1, "Last dim must be contiguous")
     B, Sq, H, D = q.shape
     paged = block_table_ is not None
-    _check(D in (64, 128), "the kv-cache path needs head_dim 64 or 128 (the cache cannot be padded in place)")
+    _padded_dim(D)
     if paged:
         _check(block_table_.dtype == torch.int32 and block_table_.is_cuda, "block_table must be int32 on CUDA")
         _check(block_table_.stride(-1) == 1, "block_table must have contiguous last dimension")

@@ -130,8 +130,20 @@ def _rotary_tables(seqlen, rot, dtype, device="cuda"):
 @pytest.mark.parametrize("paged", [False, True])
 @pytest.mark.parametrize("Sq,interleaved,causal", [(1, True, True), (1, False, False), (5, False, True), (130, True, True)])
 def test_kvcache_append_rotary_vs_oracle(api, dtype, paged, Sq, interleaved, causal):
+    _kvcache_append_rotary_case(api, dtype, paged, Sq, interleaved, causal, 128)
+
+
+@pytest.mark.parametrize("D", [32, 96])
+@pytest.mark.parametrize("Sq,paged", [(1, True), (5, False), (130, True)])
+def test_kvcache_head_dims_without_padding(api, D, Sq, paged):
+    """Head dims below the kernel's tile width go through unpadded (TMA zero-fills the tile's extra columns),
+    so the cache is appended to and read in place."""
+    _kvcache_append_rotary_case(api, torch.bfloat16, paged, Sq, False, True, D)
+
+
+def _kvcache_append_rotary_case(api, dtype, paged, Sq, interleaved, causal, D):
     torch.manual_seed(3)
-    B, H, Hk, D = 3, 8, 2, 128
+    B, H, Hk = 3, 8, 2
     cap, page = 1024, 256
     lens = torch.tensor([500, 37, 1024 - Sq], dtype=torch.int32, device="cuda")
     if paged:
