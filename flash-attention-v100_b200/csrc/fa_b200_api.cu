@@ -98,7 +98,7 @@ int check_device(int device) {
 
 // Tile width the kernels are built for: the real head_dim (any multiple of 8) is rounded up to it and TMA
 // zero-fills the columns in between (the tensor maps carry the real head_dim as their innermost extent).
-int tile_dim(int head_dim) { return head_dim <= 64 ? 64 : 128; }
+int tile_dim(int head_dim) { return head_dim <= 64 ? 64 : head_dim <= 128 ? 128 : 256; }
 
 template <int D, bool BF16, bool FEAT, bool DECODE = false, bool DROPOUT = false>
 int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
@@ -127,6 +127,8 @@ int launch_fwd(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, bool
         if (head_dim == 128) return launch_fwd_t<128, false, true, false, true>(kp, grid, stream);
         if (head_dim == 64 && bf16) return launch_fwd_t<64, true, true, false, true>(kp, grid, stream);
         if (head_dim == 64) return launch_fwd_t<64, false, true, false, true>(kp, grid, stream);
+        if (head_dim == 256 && bf16) return launch_fwd_t<256, true, true, false, true>(kp, grid, stream);
+        if (head_dim == 256) return launch_fwd_t<256, false, true, false, true>(kp, grid, stream);
     }
 #define FA_CASE(DD, BB, FF) \
     if (head_dim == DD && bf16 == BB && feat == FF) return launch_fwd_t<DD, BB, FF>(kp, grid, stream);
@@ -138,8 +140,12 @@ int launch_fwd(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, bool
     FA_CASE(64, true, true)
     FA_CASE(64, false, false)
     FA_CASE(64, false, true)
+    FA_CASE(256, true, false)
+    FA_CASE(256, true, true)
+    FA_CASE(256, false, false)
+    FA_CASE(256, false, true)
 #undef FA_CASE
-    return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (64 and 128 are)", head_dim);
+    return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built", head_dim);
 }
 
 // Decode path: packed-GQA split-KV launch + combine.
@@ -150,7 +156,9 @@ int launch_decode(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, d
     if (head_dim == 128 && !bf16) return launch_fwd_t<128, false, false, true>(kp, grid, stream);
     if (head_dim == 64 && bf16) return launch_fwd_t<64, true, false, true>(kp, grid, stream);
     if (head_dim == 64 && !bf16) return launch_fwd_t<64, false, false, true>(kp, grid, stream);
-    return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (64 and 128 are)", head_dim);
+    if (head_dim == 256 && bf16) return launch_fwd_t<256, true, false, true>(kp, grid, stream);
+    if (head_dim == 256 && !bf16) return launch_fwd_t<256, false, false, true>(kp, grid, stream);
+    return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built", head_dim);
 }
 
 int launch_combine(const fa::FwdKernelParams& kp, const fa_b200_params_t* p, cudaStream_t stream) {
@@ -162,7 +170,9 @@ int launch_combine(const fa::FwdKernelParams& kp, const fa_b200_params_t* p, cud
 #define FA_COMBINE(DD, BB)                                                                                   \
     fa::fa_combine_kernel<DD, BB><<<grid, warps * 32, 0, stream>>>(kp.o_partial, kp.lse_partial, out, p->lse, \
         kp.num_splits, p->batch, p->num_heads, p->seqlen_q, p->o_stride_b, p->o_stride_s, p->o_stride_h, p->head_dim)
-    if (tile_dim(p->head_dim) == 128 && bf16) FA_COMBINE(128, true);
+    if (tile_dim(p->head_dim) == 256 && bf16) FA_COMBINE(256, true);
+    else if (tile_dim(p->head_dim) == 256) FA_COMBINE(256, false);
+    else if (tile_dim(p->head_dim) == 128 && bf16) FA_COMBINE(128, true);
     else if (tile_dim(p->head_dim) == 128) FA_COMBINE(128, false);
     else if (bf16) FA_COMBINE(64, true);
     else FA_COMBINE(64, false);
@@ -240,7 +250,8 @@ int sm_count(int device) {
 
 // Persistent 1-D grid; work items in sectioned longest-first order (see FwdKernelParams::section_bh).
 dim3 set_launch_order(fa::FwdKernelParams& kp, int device, int batch, int heads, int heads_k, int max_seqlen_q, int max_seqlen_k, int head_dim) {
-    kp.num_m_blocks = (max_seqlen_q + 255) / 256;
+    const int item_rows = tile_dim(head_dim) == 256 ? 128 : 256;  // FwdConfig<D>::kItemRows
+    kp.num_m_blocks = (max_seqlen_q + item_rows - 1) / item_rows;
     kp.num_bh = batch * heads;
     // K+V bytes one kv head streams; keep a section's K/V within ~32 MB of the 126 MB L2
     const int64_t kv_bytes = 2ll * max_seqlen_k * head_dim * 2;
@@ -278,8 +289,6 @@ int check_common(const fa_b200_params_t* p) {
     CHECK_ARG(p->num_heads % p->num_heads_k == 0, "H_Q must be divisible by H_K for GQA/MQA");
     CHECK_ARG(p->head_dim % 8 == 0, "head dimension must be multiple of 8");
     CHECK_ARG(p->head_dim > 0 && p->head_dim <= 256, "head dimension must be <= 256");
-    if (p->head_dim > 128)
-        return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (any multiple of 8 up to 128 is)", p->head_dim);
     CHECK_ARG(p->q && p->k && p->v && p->out && p->lse, "q, k, v, out and lse must be non-NULL");
     CHECK_ARG(p->softcap >= 0.f, "softcap must be >= 0");
     CHECK_ARG((reinterpret_cast<uintptr_t>(p->out) & 15) == 0 && p->o_stride_b % 8 == 0 && p->o_stride_s % 8 == 0 &&
@@ -657,6 +666,8 @@ int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     // reference kernel/fused_mha_backward.cu:604-700
     CHECK_ARG(p->dout && p->dq && p->dk && p->dv && p->softmax_d, "dout, dq, dk, dv and softmax_d must be non-NULL");
+    if (p->head_dim > 128)
+        return fail(FA_B200_EUNSUPPORTED, "backward: head_dim %d is not built (any multiple of 8 up to 128 is)", p->head_dim);
     CHECK_ARG(p->seqlen_q > 0 && p->seqlen_k > 0, "seqlen_q / seqlen_k must be positive (the caller handles empty inputs)");
     CHECK_ARG(p->p_dropout >= 0.f && p->p_dropout < 1.f, "p_dropout must be in [0, 1)");
     CHECK_ARG(p->softcap == 0.f || p->p_dropout == 0.f, "Softcapping does not support dropout");

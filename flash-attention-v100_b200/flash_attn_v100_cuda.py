@@ -146,12 +146,11 @@ def _call(fn_name: str, params: FaB200Params, device: torch.device) -> None:
 
 
 def _padded_dim(d: int) -> int:
-    """Head dims the C layer takes: any multiple of 8 (the reference's own check, kernel/fused_mha_forward.cu:335);
-    the kernels' tiles are 64 / 128 wide and TMA zero-fills the columns past `d`, so nothing is padded here."""
+    """Head dims the C layer takes: any multiple of 8 up to 256 (the reference's own checks,
+    kernel/fused_mha_forward.cu:335-336); the kernels' tiles are 64 / 128 / 256 wide and TMA zero-fills the
+    columns past `d`, so nothing is padded here."""
     _check(d <= 256, "head dimension must be <= 256")
     _check(d % 8 == 0, "head dimension must be multiple of 8")
-    if d > 128:
-        raise NotImplementedError(f"head_dim {d} > 128 is not built yet (SURVEY 8f rank 3)")
     return d
 
 

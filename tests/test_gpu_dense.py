@@ -31,9 +31,10 @@ def op(fa_lib):
     return m
 
 
-# shapes of reference test.py:115-139 that the CPU oracle finishes in seconds (D=256 is not built yet)
-REF_SHAPES = [(1, 1, 16, 16, 16), (1, 1, 32, 32, 32), (1, 1, 64, 64, 64), (1, 1, 128, 128, 128),
-              (1, 16, 1024, 1024, 16), (1, 16, 1024, 1024, 32), (1, 16, 1024, 1024, 64), (1, 16, 1024, 1024, 128)]
+# shapes of reference test.py:115-139 that the CPU oracle finishes in seconds
+REF_SHAPES = [(1, 1, 16, 16, 16), (1, 1, 32, 32, 32), (1, 1, 64, 64, 64), (1, 1, 128, 128, 128), (1, 1, 256, 256, 256),
+              (1, 16, 1024, 1024, 16), (1, 16, 1024, 1024, 32), (1, 16, 1024, 1024, 64), (1, 16, 1024, 1024, 128),
+              (1, 16, 1024, 1024, 256)]
 
 
 @pytest.mark.parametrize("B,H,M,N,D", REF_SHAPES)
@@ -103,7 +104,7 @@ def test_sliding_window(api, window):
 
 @pytest.mark.parametrize("softcap,alibi,causal", [(30.0, False, False), (0.0, True, True), (0.0, True, False),
                                                  (20.0, True, True)])
-@pytest.mark.parametrize("D", [64, 128])
+@pytest.mark.parametrize("D", [64, 128, 256])
 def test_softcap_and_alibi(api, softcap, alibi, causal, D):
     B, H = 2, 4
     q, k, v = rand_qkv(B, 384, 384, H, 2, D, torch.bfloat16)
@@ -114,7 +115,7 @@ def test_softcap_and_alibi(api, softcap, alibi, causal, D):
     check_dense(out, None, q, k, v, causal=causal, softcap=softcap, alibi=slopes)
 
 
-@pytest.mark.parametrize("D", [16, 32, 40, 80, 96, 100])
+@pytest.mark.parametrize("D", [16, 32, 40, 80, 96, 100, 136, 192, 250, 256])
 def test_head_dims_by_padding(api, D):
     q, k, v = rand_qkv(1, 200, 264, 4, 4, D, torch.float16)
     out = api.flash_attn_func(q, k, v, causal=True)

@@ -43,7 +43,8 @@ def _visible(Sq, Sk, causal, window):
     (2, 200, 328, 2, 2, 64, True, (-1, -1), 0.5),      # Sq != Sk, ragged tiles, Sk % 8 == 0
     (1, 130, 203, 2, 1, 64, False, (-1, -1), 0.3),     # Sk % 4 != 0: unaligned Philox words and dmask rows
     (1, 512, 512, 2, 2, 128, False, (100, 30), 0.2),   # sliding window
-    (1, 96, 96, 2, 2, 32, True, (-1, -1), 0.15),       # padded head dim
+    (1, 96, 96, 2, 2, 32, True, (-1, -1), 0.15),       # head dim below the tile width
+    (1, 300, 300, 2, 2, 256, True, (-1, -1), 0.2),     # head dim 256: both D-halves must see the same mask
 ])
 def test_dense_dropout_matches_oracle(api, dtype, B, Sq, Sk, H, Hk, D, causal, window, p):
     torch.manual_seed(421)

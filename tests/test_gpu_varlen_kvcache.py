@@ -39,8 +39,18 @@ def _cu(lens, device="cuda"):
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("lens", [[5, 33, 1, 64, 300, 257, 128], [1], [700, 3]])
 def test_varlen_vs_oracle(api, op, dtype, causal, lens):
+    _varlen_case(api, op, dtype, causal, lens, 128)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("D", [32, 256])
+def test_varlen_head_dims(api, op, causal, D):
+    _varlen_case(api, op, torch.bfloat16, causal, [5, 33, 1, 64, 300, 257, 128], D)
+
+
+def _varlen_case(api, op, dtype, causal, lens, D):
     torch.manual_seed(421)
-    H, Hk, D = 4, 2, 128
+    H, Hk = 4, 2
     T = sum(lens)
     q = torch.randn(T, H, D, device="cuda", dtype=dtype)
     k = torch.randn(T, Hk, D, device="cuda", dtype=dtype)
@@ -133,7 +143,7 @@ def test_kvcache_append_rotary_vs_oracle(api, dtype, paged, Sq, interleaved, cau
     _kvcache_append_rotary_case(api, dtype, paged, Sq, interleaved, causal, 128)
 
 
-@pytest.mark.parametrize("D", [32, 96])
+@pytest.mark.parametrize("D", [32, 96, 256])
 @pytest.mark.parametrize("Sq,paged", [(1, True), (5, False), (130, True)])
 def test_kvcache_head_dims_without_padding(api, D, Sq, paged):
     """Head dims below the kernel's tile width go through unpadded (TMA zero-fills the tile's extra columns),
