@@ -25,6 +25,11 @@
 //   * warp 8: TMA producer.  warp 9: tcgen05.mma issuer.  mbarriers order everything.
 //
 // The softmax scale is applied in the epilogue (dQ, dK *= scale), and so is dropout's 1/(1-p) on dV.
+//
+// head_dim 256 ("split-D"): two 128 x 256 stationary tiles fill 128 KB of shared memory and two 256-column
+// accumulators would fill TMEM, so (a) the streamed side moves in 64-row tiles (T1, T2 are 128 x 64) through a
+// 3-slot ring, and (b) each CTA owns one 128-column half of the outputs: grid.x = 2 x blocks, CTA 2b+h
+// accumulates out[:, 128h .. 128h+128) of block b. T1 and T2 are contracted over all 256 dims by both CTAs.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -41,6 +46,8 @@ struct alignas(64) BwdKernelParams {
     CUtensorMap tm_k;
     CUtensorMap tm_v;
     CUtensorMap tm_do;
+    CUtensorMap tm_q_stat;   // head_dim 256, dQ pass only: 128-row boxes for the stationary Q / dO tiles
+    CUtensorMap tm_do_stat;  // (tm_q / tm_do / tm_k / tm_v then carry the 64-row boxes of the streamed side)
     void* dq;
     void* dk;
     void* dv;
@@ -74,18 +81,24 @@ struct alignas(64) BwdKernelParams {
 
 template <int D>
 struct BwdConfig {
-    static constexpr int kTileBytes = 128 * D * 2;
-    static constexpr int kHalfBytes = 128 * 128;
-    static constexpr int kRing = (D == 128) ? 4 : 6;  // streamed tiles in flight (B1, B2 alternate)
+    static constexpr bool kSplitD = (D == 256);           // see "split-D" in the header comment
+    static constexpr int kBTS = kSplitD ? 64 : 128;       // rows of a streamed tile (= columns of T1, T2)
+    static constexpr int kOW = kSplitD ? 128 : D;         // columns of one accumulator in this CTA
+    static constexpr int kTileBytes = 128 * D * 2;        // stationary tile
+    static constexpr int kHalfBytes = 128 * 128;          // one 64-column swizzle block of a stationary tile
+    static constexpr int kStreamBytes = kBTS * D * 2;     // streamed tile
+    static constexpr int kStreamBlk = kBTS * 128;         // one 64-column swizzle block of a streamed tile
+    static constexpr int kRing = (D == 256) ? 3 : (D == 128) ? 4 : 6;  // streamed tiles in flight (B1, B2 alternate)
     static constexpr int kSmemStat = 2 * kTileBytes;
-    static constexpr int kSmemRing = kRing * kTileBytes;
+    static constexpr int kSmemRing = kRing * kStreamBytes;
     static constexpr int kNumBars = 2 + 2 * kRing + 5;
     static constexpr int kOffBars = kSmemStat + kSmemRing;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
-    static constexpr int kOffStats = (kOffTmemPtr + 16 + 15) & ~15;  // float [2 buffers][2 kinds][128]
-    static constexpr int kSmemUsed = kOffStats + 2 * 2 * 128 * 4;
+    static constexpr int kOffStats = (kOffTmemPtr + 16 + 15) & ~15;  // float [2 buffers][2 kinds][kBTS]
+    static constexpr int kSmemUsed = kOffStats + 2 * 2 * kBTS * 4;
     static constexpr int kSmemBytes = kSmemUsed + 1024;
-    static constexpr int kTmemT1 = 0, kTmemT2 = 128, kTmemOut1 = 256, kTmemOut2 = 256 + D;
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
+    static constexpr int kTmemT1 = 0, kTmemT2 = 128, kTmemOut1 = 256, kTmemOut2 = 256 + kOW;
 };
 
 FA_DEVICE void mul2(float& a0, float& a1, float b0, float b1) {
@@ -155,7 +168,10 @@ template <int D, bool BF16, bool FEAT, bool KV_STAT, bool DROPOUT>
 __global__ void __launch_bounds__(384, 1)
 fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
     using Cfg = BwdConfig<D>;
-    constexpr int BT = 128;  // tile rows on both sides
+    constexpr int BT = 128;           // rows of the stationary block
+    constexpr int BTS = Cfg::kBTS;    // rows of a streamed tile
+    constexpr int CW = BTS / 2;       // tile columns one element-wise warpgroup handles
+    constexpr bool SPLIT = Cfg::kSplitD;
     constexpr int RING = Cfg::kRing;
 
     // ------------------------------------------------------------------ geometry (uniform over the CTA)
@@ -172,7 +188,9 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
     const int o_b = p.cu_seqlens_q ? 0 : batch;
     const int G = p.heads_per_kv;
     const int off = seqlen_k - seqlen_q;
-    const int blk = p.reverse ? p.num_blocks - 1 - (int)blockIdx.x : (int)blockIdx.x;
+    const int bx = SPLIT ? (int)blockIdx.x >> 1 : (int)blockIdx.x;
+    const int dhalf = SPLIT ? (int)blockIdx.x & 1 : 0;  // split-D: which 128-column half of the outputs is mine
+    const int blk = p.reverse ? p.num_blocks - 1 - bx : bx;
     const int x0 = blk * BT;  // first row of the stationary block (query position or key position)
     if (x0 >= (KV_STAT ? seqlen_k : seqlen_q)) return;
     const int kv_head = KV_STAT ? (int)blockIdx.y : (int)blockIdx.y / G;
@@ -181,21 +199,21 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
     // streamed tiles [t_lo, t_hi) along the other sequence, visible to at least one row of this block
     int t_lo = 0, t_hi;
     if constexpr (KV_STAT) {
-        t_hi = (seqlen_q + BT - 1) / BT;
+        t_hi = (seqlen_q + BTS - 1) / BTS;
         const int j_last = min(x0 + BT, seqlen_k) - 1;
-        if (p.window_right >= 0) t_lo = max(0, x0 - off - p.window_right) / BT;
+        if (p.window_right >= 0) t_lo = max(0, x0 - off - p.window_right) / BTS;
         if (p.window_left >= 0) {
             const int i_max = j_last - off + p.window_left;
-            t_hi = min(t_hi, i_max < 0 ? 0 : i_max / BT + 1);
+            t_hi = min(t_hi, i_max < 0 ? 0 : i_max / BTS + 1);
         }
     } else {
-        t_hi = (seqlen_k + BT - 1) / BT;
+        t_hi = (seqlen_k + BTS - 1) / BTS;
         const int i_last = min(x0 + BT, seqlen_q) - 1;
         if (p.window_right >= 0) {
             const int j_max = i_last + off + p.window_right;
-            t_hi = min(t_hi, j_max < 0 ? 0 : j_max / BT + 1);
+            t_hi = min(t_hi, j_max < 0 ? 0 : j_max / BTS + 1);
         }
-        if (p.window_left >= 0) t_lo = max(0, x0 + off - p.window_left) / BT;
+        if (p.window_left >= 0) t_lo = max(0, x0 + off - p.window_left) / BTS;
     }
     const int nt = max(t_hi - t_lo, 0);         // tiles per head
     const int n_tiles = KV_STAT ? nt * G : nt;  // the dK/dV pass streams the whole GQA group
@@ -255,27 +273,32 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
 #pragma unroll
                 for (int c = 0; c < D / 64; ++c) tma_load_4d(dst + c * Cfg::kHalfBytes, tm, bar, c * 64, h, row, b);
             };
+            auto load_stream = [&](const CUtensorMap* tm, uint32_t dst, uint32_t bar, int h, int row, int b) {
+                mbar_arrive_expect_tx(bar, Cfg::kStreamBytes);  // the streamed maps' boxes have BTS rows
+#pragma unroll
+                for (int c = 0; c < D / 64; ++c) tma_load_4d(dst + c * Cfg::kStreamBlk, tm, bar, c * 64, h, row, b);
+            };
             int ring = 0;
             auto produce = [&](const CUtensorMap* tm, int h, int row, int b) {
                 const int slot = ring % RING;
                 mbar_wait(bar_ring_empty(slot), ((ring / RING) & 1) ^ 1);
-                if (lane == 0) load_tile(tm, sRing + slot * Cfg::kTileBytes, bar_ring_full(slot), h, row, b);
+                if (lane == 0) load_stream(tm, sRing + slot * Cfg::kStreamBytes, bar_ring_full(slot), h, row, b);
                 ++ring;
             };
             auto stream_tile = [&](int t, bool second) {
                 const int g = KV_STAT ? t / nt : 0;
                 const int ti = t_lo + (KV_STAT ? t - g * nt : t);
-                if constexpr (KV_STAT) produce(second ? &p.tm_do : &p.tm_q, head0 + g, q_off + ti * BT, q_b);
-                else produce(second ? &p.tm_v : &p.tm_k, kv_head, k_off + ti * BT, k_b);
+                if constexpr (KV_STAT) produce(second ? &p.tm_do : &p.tm_q, head0 + g, q_off + ti * BTS, q_b);
+                else produce(second ? &p.tm_v : &p.tm_k, kv_head, k_off + ti * BTS, k_b);
             };
             if (lane == 0) {
                 if constexpr (KV_STAT) load_tile(&p.tm_k, sStat, bar_a_full(0), kv_head, k_off + x0, k_b);
-                else load_tile(&p.tm_q, sStat, bar_a_full(0), head0, q_off + x0, q_b);
+                else load_tile(SPLIT ? &p.tm_q_stat : &p.tm_q, sStat, bar_a_full(0), head0, q_off + x0, q_b);
             }
             stream_tile(0, false);
             if (lane == 0) {
                 if constexpr (KV_STAT) load_tile(&p.tm_v, sStat + Cfg::kTileBytes, bar_a_full(1), kv_head, k_off + x0, k_b);
-                else load_tile(&p.tm_do, sStat + Cfg::kTileBytes, bar_a_full(1), head0, q_off + x0, q_b);
+                else load_tile(SPLIT ? &p.tm_do_stat : &p.tm_do, sStat + Cfg::kTileBytes, bar_a_full(1), head0, q_off + x0, q_b);
             }
             stream_tile(0, true);
             for (int t = 1; t < n_tiles; ++t) {
@@ -287,20 +310,27 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
         // ============================================================ MMA issuer
         reg_dec<48>();
         if (n_tiles > 0) {
-            constexpr uint32_t idesc_t = umma_idesc_f16(BF16, BT, BT, false, false);
-            constexpr uint32_t idesc_o = umma_idesc_f16(BF16, BT, D, false, true);
+            constexpr uint32_t idesc_t = umma_idesc_f16(BF16, BT, BTS, false, false);
+            constexpr uint32_t idesc_o = umma_idesc_f16(BF16, BT, Cfg::kOW, false, true);
             const uint32_t tT1 = tmem_base + Cfg::kTmemT1, tT2 = tmem_base + Cfg::kTmemT2;
             const uint32_t tO1 = tmem_base + Cfg::kTmemOut1, tO2 = tmem_base + Cfg::kTmemOut2;
             constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
             constexpr uint32_t kLoKmajor = 1u << 16;
-            constexpr uint32_t kLoMn = (uint32_t)(Cfg::kHalfBytes >> 4) << 16;
+            constexpr uint32_t kLoMn = (uint32_t)(Cfg::kStreamBlk >> 4) << 16;
             auto lo_addr = [](uint32_t saddr) { return (saddr & 0x3FFFFu) >> 4; };
-            auto slot_addr = [&](int r) { return sRing + (r % RING) * Cfg::kTileBytes; };
+            auto slot_addr = [&](int r) { return sRing + (r % RING) * Cfg::kStreamBytes; };
+            // second GEMMs: B = the streamed tile as an MN-major operand; split-D takes this CTA's 128 columns of it
+            auto mn_lo = [&](int r) { return lo_addr(slot_addr(r) + (SPLIT ? dhalf * 2 * Cfg::kStreamBlk : 0)) | kLoMn; };
+            auto issue_o = [&](uint32_t d_tmem, uint32_t a_tmem, int r, uint32_t acc) {
+                if constexpr (SPLIT) umma_issue_ts_split32(d_tmem, a_tmem, mn_lo(r), 0, kDescHi, idesc_o, acc);
+                else umma_issue_ts_split(d_tmem, a_tmem, mn_lo(r), 0, kDescHi, idesc_o, acc);
+            };
             auto wait_full = [&](int r) { mbar_wait(bar_ring_full(r % RING), (r / RING) & 1); };
             auto issue_t = [&](uint32_t d_tmem, int a_idx, int r) {  // d = A[a_idx] * B(ring r)^T
                 const uint32_t a_lo = lo_addr(sStat + a_idx * Cfg::kTileBytes) | kLoKmajor;
                 const uint32_t b_lo = lo_addr(slot_addr(r)) | kLoKmajor;
-                if constexpr (D == 128) umma_issue_qk_d128(d_tmem, a_lo, b_lo, kDescHi, kDescHi, idesc_t);
+                if constexpr (D == 256) umma_issue_t_d256_n64(d_tmem, a_lo, b_lo, kDescHi, kDescHi, idesc_t);
+                else if constexpr (D == 128) umma_issue_qk_d128(d_tmem, a_lo, b_lo, kDescHi, kDescHi, idesc_t);
                 else umma_issue_qk_d64(d_tmem, a_lo, b_lo, kDescHi, kDescHi, idesc_t);
             };
             mbar_wait(bar_a_full(0), 0);
@@ -318,7 +348,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                 mbar_wait(bar_p_ready, ph);  // T1(t) is in registers; in the dK/dV pass P(t) sits in T1's columns
                 tc_fence_after();
                 if constexpr (KV_STAT)
-                    umma_issue_ts_split(tO2, tT1, lo_addr(slot_addr(2 * t + 1)) | kLoMn, 0, kDescHi, idesc_o, t > 0 ? 1u : 0u);
+                    issue_o(tO2, tT1, 2 * t + 1, t > 0 ? 1u : 0u);
                 if (t + 1 < n_tiles) {  // executes after the P read above (tcgen05 ops run in issue order)
                     wait_full(2 * t + 2);
                     tc_fence_after();
@@ -327,7 +357,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                 }
                 mbar_wait(bar_ds_ready, ph);
                 tc_fence_after();
-                umma_issue_ts_split(tO1, tT2, lo_addr(slot_addr(2 * t)) | kLoMn, 0, kDescHi, idesc_o, t > 0 ? 1u : 0u);
+                issue_o(tO1, tT2, 2 * t, t > 0 ? 1u : 0u);
                 umma_commit_elect(bar_ring_empty((2 * t) % RING));
                 umma_commit_elect(bar_ring_empty((2 * t + 1) % RING));
                 if (t + 1 < n_tiles) {
@@ -345,8 +375,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
         const int wg = warp >> 2;                  // column half of every tile
         const int r = (warp & 3) * 32 + lane;      // row of the stationary block == TMEM lane
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t tT1 = tmem_base + lane_off + Cfg::kTmemT1 + wg * 64;
-        const uint32_t tT2 = tmem_base + lane_off + Cfg::kTmemT2 + wg * 64;
+        const uint32_t tT1 = tmem_base + lane_off + Cfg::kTmemT1 + wg * CW;
+        const uint32_t tT2 = tmem_base + lane_off + Cfg::kTmemT2 + wg * CW;
         const int x = x0 + r;  // this thread's query position (dQ pass) or key position (dK/dV pass)
         const float sl2 = FEAT ? 1.0f : p.scale_log2;
 
@@ -375,23 +405,23 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
         }
         const float inv_cap = (FEAT && p.softcap > 0.f) ? 1.0f / p.softcap : 0.f;
 
-        // dK/dV pass: column statistics of streamed tile t, one value per thread (256 threads = 128 x {lse, delta})
+        // dK/dV pass: column statistics of streamed tile t, one value per thread (2*BTS threads = BTS x {lse, delta})
         auto load_stat = [&](int t) -> float {
             const int g = t / max(nt, 1);
-            const int i = (t_lo + t - g * nt) * BT + (threadIdx.x & 127);
-            if (t >= n_tiles || i >= seqlen_q) return 0.f;
+            const int i = (t_lo + t - g * nt) * BTS + ((int)threadIdx.x % BTS);
+            if (t >= n_tiles || i >= seqlen_q || (int)threadIdx.x >= 2 * BTS) return 0.f;
             const int64_t idx = o_b * p.lse_stride_b + (int64_t)(head0 + g) * p.lse_stride_h + q_off + i;
-            return threadIdx.x < 128 ? neg_lse_log2(p.lse[idx]) : -p.delta[idx];
+            return (int)threadIdx.x < BTS ? neg_lse_log2(p.lse[idx]) : -p.delta[idx];
         };
         float stat_next = 0.f;
         if constexpr (KV_STAT) stat_next = load_stat(0);
 
         for (int t = 0; t < n_tiles; ++t) {
             const int g = KV_STAT ? t / nt : 0;
-            const int c0 = (t_lo + (KV_STAT ? t - g * nt : t)) * BT + wg * 64;  // streamed index of my first column
-            const float* tab = sTab + (t & 1) * 256;
+            const int c0 = (t_lo + (KV_STAT ? t - g * nt : t)) * BTS + wg * CW;  // streamed index of my first column
+            const float* tab = sTab + (t & 1) * (2 * BTS);
             if constexpr (KV_STAT) {
-                sTab[(t & 1) * 256 + threadIdx.x] = stat_next;
+                if ((int)threadIdx.x < 2 * BTS) sTab[(t & 1) * (2 * BTS) + threadIdx.x] = stat_next;
                 named_bar_sync(1, 256);
                 stat_next = load_stat(t + 1);
             }
@@ -403,19 +433,20 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
             // ---- T1 -> P
             mbar_wait(bar_t1_full, t & 1);
             tc_fence_after();
-            float pv[64];
-            tmem_ld_x64_wait(tT1, reinterpret_cast<uint32_t*>(pv));
+            float pv[CW];
+            if constexpr (CW == 64) tmem_ld_x64_wait(tT1, reinterpret_cast<uint32_t*>(pv));
+            else tmem_ld_x32_wait(tT1, reinterpret_cast<uint32_t*>(pv));
             if constexpr (!KV_STAT) {  // dQ pass: nothing is written back over T1, release it right away
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_p_ready);
             }
-            uint32_t fac[FEAT ? 32 : 1];  // softcap: (1 - tanh^2) as f16 pairs
+            uint32_t fac[FEAT ? CW / 2 : 1];  // softcap: (1 - tanh^2) as f16 pairs
             if constexpr (FEAT) {
                 // reference order (include/mat_mul.h:111-117): scale, ALiBi, softcap
                 const int rel0 = KV_STAT ? c0 + off - x : x + off - c0;  // i + off - j at column 0
 #pragma unroll
-                for (int c = 0; c < 64; c += 2) {
+                for (int c = 0; c < CW; c += 2) {
                     float u[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
@@ -432,17 +463,17 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                     fac[c / 2] = pack_half2(u[0], u[1]);
                 }
             }
-            const bool need_mask = (c0 < lo) || ((unsigned)(c0 + 64 - lo) > width);
+            const bool need_mask = (c0 < lo) || ((unsigned)(c0 + CW - lo) > width);
             if (__any_sync(0xffffffffu, need_mask)) {
                 const int base = c0 - lo;
 #pragma unroll
-                for (int c = 0; c < 64; ++c) pv[c] = ((unsigned)(base + c) < width) ? pv[c] : -INFINITY;
+                for (int c = 0; c < CW; ++c) pv[c] = ((unsigned)(base + c) < width) ? pv[c] : -INFINITY;
             }
 #pragma unroll
-            for (int c = 0; c < 64; c += 4) {
+            for (int c = 0; c < CW; c += 4) {
                 float n0, n1, n2, n3;
                 if constexpr (KV_STAT) {
-                    const float4 nl = *reinterpret_cast<const float4*>(tab + wg * 64 + c);
+                    const float4 nl = *reinterpret_cast<const float4*>(tab + wg * CW + c);
                     n0 = nl.x, n1 = nl.y, n2 = nl.z, n3 = nl.w;
                 } else {
                     n0 = n1 = n2 = n3 = row_nl;
@@ -455,12 +486,12 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                 pv[c + 3] = ex2_approx(pv[c + 3]);
             }
             // dropout keep bits for my 64 columns (reference include/softmax.h:276-291: same index as the forward)
-            uint32_t keep[2] = {0xffffffffu, 0xffffffffu};
+            uint32_t keep[2] = {0xffffffffu, 0xffffffffu};  // CW / 32 words are used
             if constexpr (DROPOUT) {
                 const uint32_t k0 = (uint32_t)p.drop_seed, k1 = (uint32_t)(p.drop_seed >> 32);
                 if constexpr (KV_STAT) {  // columns are query rows: every element has its own counter
 #pragma unroll 1
-                    for (int w = 0; w < 2; ++w) {
+                    for (int w = 0; w < CW / 32; ++w) {
                         uint32_t bits = 0u;
 #pragma unroll 4
                         for (int c = 0; c < 32; ++c) {
@@ -472,7 +503,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                     }
                 } else {
 #pragma unroll
-                    for (int w = 0; w < 2; ++w) {
+                    for (int w = 0; w < CW / 32; ++w) {
                         const uint64_t idx0 = (uint64_t)(q_off + x) * (uint64_t)p.seqlen_k + (uint64_t)(c0 + w * 32);
                         const uint32_t sh = (uint32_t)idx0 & 3u;
                         const uint64_t ctr0 = p.drop_offset + (idx0 >> 2);
@@ -485,9 +516,9 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                 }
             }
             if constexpr (KV_STAT) {  // P (after dropout, unscaled) -> TMEM over my half of T1
-                uint32_t pk[32];
+                uint32_t pk[CW / 2];
 #pragma unroll
-                for (int c = 0; c < 64; c += 2) {
+                for (int c = 0; c < CW; c += 2) {
                     float a = pv[c], b = pv[c + 1];
                     if constexpr (DROPOUT) {
                         a = (keep[c >> 5] >> (c & 31)) & 1u ? a : 0.f;
@@ -495,7 +526,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                     }
                     pk[c / 2] = pack2<BF16>(a, b);
                 }
-                tmem_st_x32(tT1, pk);
+                if constexpr (CW == 64) tmem_st_x32(tT1, pk);
+                else tmem_st_x16(tT1, pk);
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
@@ -505,9 +537,9 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
             // ---- T2 -> dS = P * (keep * rp * dP - delta)       (reference include/softmax.h:293-294)
             mbar_wait(bar_t2_full, t & 1);
             tc_fence_after();
-            uint32_t dsk[32];
+            uint32_t dsk[CW / 2];
 #pragma unroll
-            for (int hc = 0; hc < 2; ++hc) {
+            for (int hc = 0; hc < CW / 32; ++hc) {
                 float dp[32];
                 tmem_ld_x32_wait(tT2 + hc * 32, reinterpret_cast<uint32_t*>(dp));
 #pragma unroll
@@ -520,7 +552,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                     }
                     float d0, d1;
                     if constexpr (KV_STAT) {
-                        const float2 nd = *reinterpret_cast<const float2*>(tab + 128 + wg * 64 + cc);
+                        const float2 nd = *reinterpret_cast<const float2*>(tab + BTS + wg * CW + cc);
                         d0 = nd.x, d1 = nd.y;
                     } else {
                         d0 = d1 = -row_delta;
@@ -534,7 +566,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                     dsk[cc / 2] = pack2<BF16>(a, b);
                 }
             }
-            tmem_st_x32(tT2, dsk);
+            if constexpr (CW == 64) tmem_st_x32(tT2, dsk);
+            else tmem_st_x16(tT2, dsk);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -547,14 +580,15 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
             mbar_wait(bar_out_full, 0);
             tc_fence_after();
         }
-        constexpr int HALF = D / 2;
+        constexpr int HALF = Cfg::kOW / 2;
+        const int col_base = SPLIT ? dhalf * Cfg::kOW : 0;  // first output column this CTA owns
         auto store_out = [&](uint32_t tmem_col, void* base, int64_t sb, int64_t ss, int64_t sh, int head, int row_off,
                              float mult) {
-            uint16_t* dst = static_cast<uint16_t*>(base) + o_b * sb + (int64_t)(row_off + x) * ss + (int64_t)head * sh + wg * HALF;
+            uint16_t* dst = static_cast<uint16_t*>(base) + o_b * sb + (int64_t)(row_off + x) * ss + (int64_t)head * sh + col_base + wg * HALF;
             const bool wide_ok = __all_sync(0xffffffffu, (reinterpret_cast<uintptr_t>(dst) & 31) == 0);
 #pragma unroll
             for (int c = 0; c < HALF; c += 32) {
-                const int col = wg * HALF + c;  // columns [head_dim, D) are the tile's zero padding
+                const int col = col_base + wg * HALF + c;  // columns [head_dim, D) are the tile's zero padding
                 if (col >= p.head_dim) break;
                 float o[32];
                 if (n_tiles > 0) {

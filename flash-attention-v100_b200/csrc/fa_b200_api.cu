@@ -656,8 +656,10 @@ int launch_bwd(const fa::BwdKernelParams& kp, int real_head_dim, bool bf16, bool
     FA_BCASE(128, false)
     FA_BCASE(64, true)
     FA_BCASE(64, false)
+    FA_BCASE(256, true)
+    FA_BCASE(256, false)
 #undef FA_BCASE
-    return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built (64 and 128 are)", head_dim);
+    return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built", head_dim);
 }
 
 int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
@@ -666,8 +668,6 @@ int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     // reference kernel/fused_mha_backward.cu:604-700
     CHECK_ARG(p->dout && p->dq && p->dk && p->dv && p->softmax_d, "dout, dq, dk, dv and softmax_d must be non-NULL");
-    if (p->head_dim > 128)
-        return fail(FA_B200_EUNSUPPORTED, "backward: head_dim %d is not built (any multiple of 8 up to 128 is)", p->head_dim);
     CHECK_ARG(p->seqlen_q > 0 && p->seqlen_k > 0, "seqlen_q / seqlen_k must be positive (the caller handles empty inputs)");
     CHECK_ARG(p->p_dropout >= 0.f && p->p_dropout < 1.f, "p_dropout must be in [0, 1)");
     CHECK_ARG(p->softcap == 0.f || p->p_dropout == 0.f, "Softcapping does not support dropout");
@@ -703,10 +703,18 @@ int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
     const int64_t rows_q = varlen ? p->total_q : p->seqlen_q;
     const int64_t rows_k = varlen ? p->total_k : p->seqlen_k;
     const int64_t nb = varlen ? 1 : p->batch;
-    if (int rc = make_tmap(&kp.tm_q, p->dtype, p->q, p->head_dim, p->num_heads, rows_q, nb, p->q_stride_h, p->q_stride_s, varlen ? 0 : p->q_stride_b, "q")) return rc;
-    if (int rc = make_tmap(&kp.tm_do, p->dtype, p->dout, p->head_dim, p->num_heads, rows_q, nb, p->do_stride_h, p->do_stride_s, varlen ? 0 : p->do_stride_b, "dout")) return rc;
-    if (int rc = make_tmap(&kp.tm_k, p->dtype, p->k, p->head_dim, p->num_heads_k, rows_k, nb, p->k_stride_h, p->k_stride_s, varlen ? 0 : p->k_stride_b, "k")) return rc;
-    if (int rc = make_tmap(&kp.tm_v, p->dtype, p->v, p->head_dim, p->num_heads_k, rows_k, nb, p->v_stride_h, p->v_stride_s, varlen ? 0 : p->v_stride_b, "v")) return rc;
+    // head_dim 256 streams 64-row tiles (BwdConfig<256>::kBTS); the stationary side always uses 128-row boxes
+    const bool split_d = tile_dim(p->head_dim) == 256;
+    const int stream_rows = split_d ? 64 : 128;
+    auto map_q = [&](CUtensorMap* tm, int box_rows) { return make_tmap(tm, p->dtype, p->q, p->head_dim, p->num_heads, rows_q, nb, p->q_stride_h, p->q_stride_s, varlen ? 0 : p->q_stride_b, "q", 1, box_rows); };
+    auto map_do = [&](CUtensorMap* tm, int box_rows) { return make_tmap(tm, p->dtype, p->dout, p->head_dim, p->num_heads, rows_q, nb, p->do_stride_h, p->do_stride_s, varlen ? 0 : p->do_stride_b, "dout", 1, box_rows); };
+    auto map_k = [&](CUtensorMap* tm, int box_rows) { return make_tmap(tm, p->dtype, p->k, p->head_dim, p->num_heads_k, rows_k, nb, p->k_stride_h, p->k_stride_s, varlen ? 0 : p->k_stride_b, "k", 1, box_rows); };
+    auto map_v = [&](CUtensorMap* tm, int box_rows) { return make_tmap(tm, p->dtype, p->v, p->head_dim, p->num_heads_k, rows_k, nb, p->v_stride_h, p->v_stride_s, varlen ? 0 : p->v_stride_b, "v", 1, box_rows); };
+    // dK/dV pass: K, V stationary; Q, dO streamed
+    if (int rc = map_q(&kp.tm_q, stream_rows)) return rc;
+    if (int rc = map_do(&kp.tm_do, stream_rows)) return rc;
+    if (int rc = map_k(&kp.tm_k, 128)) return rc;
+    if (int rc = map_v(&kp.tm_v, 128)) return rc;
     kp.dq = p->dq; kp.dk = p->dk; kp.dv = p->dv;
     kp.dq_stride_b = p->dq_stride_b; kp.dq_stride_s = p->dq_stride_s; kp.dq_stride_h = p->dq_stride_h;
     kp.dk_stride_b = p->dk_stride_b; kp.dk_stride_s = p->dk_stride_s; kp.dk_stride_h = p->dk_stride_h;
@@ -763,14 +771,20 @@ int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
     {
         kp.num_blocks = (p->seqlen_k + 127) / 128;
         kp.reverse = 0;
-        dim3 grid(kp.num_blocks, p->num_heads_k, p->batch);
+        dim3 grid(kp.num_blocks * (split_d ? 2 : 1), p->num_heads_k, p->batch);
         if (int rc = launch_bwd<true>(kp, p->head_dim, bf16, feat, dropout, grid, stream)) return rc;
     }
     // 3. dQ pass: one CTA per (128-query block, head, batch)
     {
         kp.num_blocks = (p->seqlen_q + 127) / 128;
         kp.reverse = wr >= 0 ? 1 : 0;
-        dim3 grid(kp.num_blocks, p->num_heads, p->batch);
+        if (split_d) {  // dQ pass: Q, dO stationary (128-row boxes); K, V streamed in 64-row tiles
+            if (int rc = map_q(&kp.tm_q_stat, 128)) return rc;
+            if (int rc = map_do(&kp.tm_do_stat, 128)) return rc;
+            if (int rc = map_k(&kp.tm_k, stream_rows)) return rc;
+            if (int rc = map_v(&kp.tm_v, stream_rows)) return rc;
+        }
+        dim3 grid(kp.num_blocks * (split_d ? 2 : 1), p->num_heads, p->batch);
         if (int rc = launch_bwd<false>(kp, p->head_dim, bf16, feat, dropout, grid, stream)) return rc;
     }
     return 0;

@@ -77,8 +77,12 @@ def test_argument_errors_use_the_c_error_convention(fa_lib):
     p.dtype, p.batch, p.num_heads, p.num_heads_k, p.head_dim = 1, 1, 3, 2, 128
     assert fa_lib.fa_b200_kvcache_fwd(ctypes.byref(p), None) == -1
     assert b"divisible" in fa_lib.fa_b200_last_error()
-    p.num_heads, p.head_dim = 4, 256
-    assert fa_lib.fa_b200_fwd(ctypes.byref(p), None) == -2  # valid in the reference API, not built yet
+    p.num_heads, p.head_dim = 4, 264
+    assert fa_lib.fa_b200_fwd(ctypes.byref(p), None) == -1
+    assert b"<= 256" in fa_lib.fa_b200_last_error()  # reference kernel/fused_mha_forward.cu:336
+    p.head_dim = 100
+    assert fa_lib.fa_b200_fwd(ctypes.byref(p), None) == -1
+    assert b"multiple of 8" in fa_lib.fa_b200_last_error()  # reference :335
     assert fa_lib.fa_b200_fwd(None, None) == -1
     assert fa_lib.fa_b200_workspace_bytes(None, 2) == 0
 

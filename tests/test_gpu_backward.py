@@ -39,8 +39,8 @@ def _rule(got, ref, naive, name):
     assert err <= 3.0 * err_naive + 1e-4, f"{name}: err {err:.3e} > 3 * naive {err_naive:.3e} + 1e-4"
 
 
-REF_SHAPES = [(1, 1, 16, 16, 16), (1, 1, 64, 64, 64), (1, 1, 128, 128, 128), (1, 8, 512, 512, 32),
-              (1, 8, 1024, 1024, 64), (1, 8, 1024, 1024, 128)]
+REF_SHAPES = [(1, 1, 16, 16, 16), (1, 1, 64, 64, 64), (1, 1, 128, 128, 128), (1, 1, 256, 256, 256), (1, 8, 512, 512, 32),
+              (1, 8, 1024, 1024, 64), (1, 8, 1024, 1024, 128), (1, 4, 1024, 1024, 256)]
 
 
 @pytest.mark.parametrize("B,H,M,N,D", REF_SHAPES)
@@ -118,6 +118,11 @@ def _autograd_case(api, dtype, B, Sq, Sk, H, Hk, D, tol_scale=1.0, **kw):
     (2, 96, 96, 2, 2, 40, dict(causal=True)),                           # padded head dim
     (1, 256, 256, 4, 2, 128, dict(softcap=15.0)),
     (1, 256, 256, 4, 4, 64, dict(causal=True, softcap=5.0)),
+    (1, 256, 256, 2, 2, 256, dict(causal=True)),                        # head dim 256: 64-row streamed tiles, D-split CTAs
+    (2, 200, 328, 4, 2, 256, dict()),                                   # + GQA, ragged tiles, Sq < Sk
+    (1, 328, 200, 2, 1, 192, dict(causal=True)),                        # 128 < D < 256, rows without any key
+    (1, 512, 512, 2, 2, 256, dict(window_size=(100, 30))),
+    (1, 256, 256, 2, 2, 256, dict(causal=True, softcap=10.0)),
 ])
 def test_autograd_matches_oracle(api, dtype, B, Sq, Sk, H, Hk, D, kw):
     _autograd_case(api, dtype, B, Sq, Sk, H, Hk, D, **kw)
@@ -135,6 +140,7 @@ def test_autograd_alibi(api, dtype):
     (2, 256, 256, 4, 2, 128, True, 0.1),
     (1, 200, 328, 2, 2, 64, False, 0.3),
     (1, 130, 203, 2, 1, 64, True, 0.25),   # Sk % 4 != 0: unaligned Philox words in both passes
+    (1, 200, 264, 2, 1, 256, True, 0.2),   # head dim 256
 ])
 def test_autograd_dropout(api, dtype, B, Sq, Sk, H, Hk, D, causal, p):
     _autograd_case(api, dtype, B, Sq, Sk, H, Hk, D, tol_scale=1.0 / (1 - p), causal=causal, dropout_p=p)
@@ -143,9 +149,18 @@ def test_autograd_dropout(api, dtype, B, Sq, Sk, H, Hk, D, causal, p):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("kw", [dict(causal=True), dict(), dict(causal=True, dropout_p=0.2), dict(window_size=(64, 0))])
 def test_varlen_autograd_matches_oracle(api, dtype, kw):
+    _varlen_autograd_case(api, dtype, kw, 128)
+
+
+@pytest.mark.parametrize("kw", [dict(causal=True), dict(window_size=(64, 0))])
+def test_varlen_autograd_head_dim_256(api, kw):
+    _varlen_autograd_case(api, torch.bfloat16, kw, 256)
+
+
+def _varlen_autograd_case(api, dtype, kw, D):
     torch.manual_seed(421)
     lens = [37, 256, 1, 300, 129]
-    H, Hk, D = 4, 2, 128
+    H, Hk = 4, 2
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
     T = sum(lens)
     q = torch.randn(T, H, D, device="cuda", dtype=dtype, requires_grad=True)
