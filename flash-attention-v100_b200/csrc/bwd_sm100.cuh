@@ -39,6 +39,13 @@
 
 #include "fwd_sm100.cuh"
 
+#ifndef FA_BWD_EMU_PERIOD
+#define FA_BWD_EMU_PERIOD 4  // of every FA_BWD_EMU_PERIOD pairs of exponentials ...
+#endif
+#ifndef FA_BWD_EMU_COUNT
+#define FA_BWD_EMU_COUNT 1   // ... this many are evaluated on the FMA pipes instead of the MUFU
+#endif
+
 namespace fa {
 
 struct alignas(64) BwdKernelParams {
@@ -88,7 +95,9 @@ struct BwdConfig {
     static constexpr int kHalfBytes = 128 * 128;          // one 64-column swizzle block of a stationary tile
     static constexpr int kStreamBytes = kBTS * D * 2;     // streamed tile
     static constexpr int kStreamBlk = kBTS * 128;         // one 64-column swizzle block of a streamed tile
-    static constexpr int kRing = (D == 256) ? 3 : (D == 128) ? 4 : 6;  // streamed tiles in flight (B1, B2 alternate)
+    // Streamed tiles in flight (B1, B2 alternate). B1(t) is read by T1(t) early in step t-1 and by the out1 GEMM at
+    // the very end of step t, so full overlap needs B1 of three steps and B2 of two resident at once: 5 slots.
+    static constexpr int kRing = (D == 256) ? 3 : (D == 128) ? 5 : 10;
     static constexpr int kSmemStat = 2 * kTileBytes;
     static constexpr int kSmemRing = kRing * kStreamBytes;
     static constexpr int kNumBars = 2 + 2 * kRing + 5;
@@ -96,7 +105,9 @@ struct BwdConfig {
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
     static constexpr int kOffStats = (kOffTmemPtr + 16 + 15) & ~15;  // float [2 buffers][2 kinds][kBTS]
     static constexpr int kSmemUsed = kOffStats + 2 * 2 * kBTS * 4;
-    static constexpr int kSmemBytes = kSmemUsed + 1024;
+    // No slack for manual alignment: the dynamic shared window is declared __align__(1024) and the kernel traps
+    // if the runtime ever hands it a base that is not (the 128B swizzle needs 1024-byte aligned tiles).
+    static constexpr int kSmemBytes = kSmemUsed;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
     static constexpr int kTmemT1 = 0, kTmemT2 = 128, kTmemOut1 = 256, kTmemOut2 = 256 + kOW;
 };
@@ -218,10 +229,10 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
     const int nt = max(t_hi - t_lo, 0);         // tiles per head
     const int n_tiles = KV_STAT ? nt * G : nt;  // the dK/dV pass streams the whole GQA group
 
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_raw_u32 = smem_u32(smem_raw);
-    const uint32_t sbase = (smem_raw_u32 + 1023u) & ~1023u;
-    uint8_t* sgen = smem_raw + (sbase - smem_raw_u32);
+    extern __shared__ __align__(1024) uint8_t smem_bwd_raw[];
+    const uint32_t sbase = smem_u32(smem_bwd_raw);
+    if ((sbase & 1023u) != 0u) __trap();  // see BwdConfig::kSmemBytes
+    uint8_t* sgen = smem_bwd_raw;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
@@ -406,13 +417,17 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
         const float inv_cap = (FEAT && p.softcap > 0.f) ? 1.0f / p.softcap : 0.f;
 
         // dK/dV pass: column statistics of streamed tile t, one value per thread (2*BTS threads = BTS x {lse, delta})
+        // The load returns the RAW value: converting it here would make the warp wait for the global load before it
+        // starts on the current tile (ncu round 1: 8 % of the pass's samples); stat_conv runs one tile later.
+        const bool stat_is_lse = (int)threadIdx.x < BTS;
+        const float* stat_src = stat_is_lse ? p.lse : p.delta;
         auto load_stat = [&](int t) -> float {
             const int g = t / max(nt, 1);
             const int i = (t_lo + t - g * nt) * BTS + ((int)threadIdx.x % BTS);
             if (t >= n_tiles || i >= seqlen_q || (int)threadIdx.x >= 2 * BTS) return 0.f;
-            const int64_t idx = o_b * p.lse_stride_b + (int64_t)(head0 + g) * p.lse_stride_h + q_off + i;
-            return (int)threadIdx.x < BTS ? neg_lse_log2(p.lse[idx]) : -p.delta[idx];
+            return stat_src[o_b * p.lse_stride_b + (int64_t)(head0 + g) * p.lse_stride_h + q_off + i];
         };
+        auto stat_conv = [&](float raw) -> float { return stat_is_lse ? neg_lse_log2(raw) : -raw; };
         float stat_next = 0.f;
         if constexpr (KV_STAT) stat_next = load_stat(0);
 
@@ -421,7 +436,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
             const int c0 = (t_lo + (KV_STAT ? t - g * nt : t)) * BTS + wg * CW;  // streamed index of my first column
             const float* tab = sTab + (t & 1) * (2 * BTS);
             if constexpr (KV_STAT) {
-                if ((int)threadIdx.x < 2 * BTS) sTab[(t & 1) * (2 * BTS) + threadIdx.x] = stat_next;
+                if ((int)threadIdx.x < 2 * BTS) sTab[(t & 1) * (2 * BTS) + threadIdx.x] = stat_conv(stat_next);
                 named_bar_sync(1, 256);
                 stat_next = load_stat(t + 1);
             }
@@ -480,10 +495,16 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                 }
                 fma2(pv[c], pv[c + 1], sl2, sl2, n0, n1);
                 fma2(pv[c + 2], pv[c + 3], sl2, sl2, n2, n3);
-                pv[c] = ex2_approx(pv[c]);
-                pv[c + 1] = ex2_approx(pv[c + 1]);
-                pv[c + 2] = ex2_approx(pv[c + 2]);
-                pv[c + 3] = ex2_approx(pv[c + 3]);
+                // FA_BWD_EMU_COUNT of every FA_BWD_EMU_PERIOD pairs go to the FMA pipes (ex2_emu2), the rest to the MUFU
+#pragma unroll
+                for (int h = 0; h < 4; h += 2) {
+                    if (FA_BWD_EMU_COUNT > 0 && (((c + h) / 2) % FA_BWD_EMU_PERIOD) >= FA_BWD_EMU_PERIOD - FA_BWD_EMU_COUNT) {
+                        ex2_emu2(pv[c + h], pv[c + h + 1]);
+                    } else {
+                        pv[c + h] = ex2_approx(pv[c + h]);
+                        pv[c + h + 1] = ex2_approx(pv[c + h + 1]);
+                    }
+                }
             }
             // dropout keep bits for my 64 columns (reference include/softmax.h:276-291: same index as the forward)
             uint32_t keep[2] = {0xffffffffu, 0xffffffffu};  // CW / 32 words are used

@@ -1,7 +1,7 @@
 /*
- * fa_b200.h -- C ABI of the B200-native FlashAttention-2 forward (libfa_b200.so).
+ * fa_b200.h -- C ABI of the B200-native FlashAttention-2 forward and backward (libfa_b200.so).
  *
- * This is the drop-in boundary for the forward hot path of ai-bond/flash-attention-v100.
+ * This is the drop-in boundary for the attention hot path of ai-bond/flash-attention-v100.
  * Each entry point replaces one function of the reference's operator layer (the pybind11 module
  * `flash_attn_v100_cuda`, reference kernel/fused_mha_api.cpp:17-33; C++ declarations in reference
  * include/mha.h):
@@ -80,7 +80,8 @@ typedef struct fa_b200_params {
                             (paged: block_table_cols * page_size) */
     int32_t num_heads;   /* query heads */
     int32_t num_heads_k; /* key/value heads; num_heads % num_heads_k == 0 */
-    int32_t head_dim;    /* 64 or 128 in this build (the Python layer pads smaller dims) */
+    int32_t head_dim;    /* any multiple of 8 up to 256 (reference kernel/fused_mha_forward.cu:335-336); the
+                            kernels' tiles are 64 / 128 / 256 wide, TMA zero-fills the columns in between */
     int32_t total_q;     /* varlen: rows of q; else 0 */
     int32_t total_k;     /* varlen non-paged: rows of k; else 0 */
 
