@@ -100,7 +100,7 @@ struct BwdConfig {
     static constexpr int kRing = (D == 256) ? 3 : (D == 128) ? 5 : 10;
     static constexpr int kSmemStat = 2 * kTileBytes;
     static constexpr int kSmemRing = kRing * kStreamBytes;
-    static constexpr int kNumBars = 2 + 2 * kRing + 5;
+    static constexpr int kNumBars = 2 + 2 * kRing + 6;
     static constexpr int kOffBars = kSmemStat + kSmemRing;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
     static constexpr int kOffStats = (kOffTmemPtr + 16 + 15) & ~15;  // float [2 buffers][2 kinds][kBTS]
@@ -134,28 +134,56 @@ FA_DEVICE float neg_lse_log2(float lse) {
     return (lse > -1e29f && lse < 1e30f) ? -lse * kLog2e : 0.f;
 }
 
-// delta[row] = sum_d O[row, d] * dO[row, d] in fp32 (reference include/product.h:9-96). One warp per
-// (batch, head, position) row; this is also the `softmax_d` tensor the operator returns.
+// delta[row] = sum_d O[row, d] * dO[row, d] in fp32 (reference include/product.h:9-96); this is also the
+// `softmax_d` tensor the operator returns. HBM-bound (reads O and dO once): a row is shared by LPR = head_dim/8
+// lanes (rounded up to a power of two) with one 16-byte load each, so a warp covers 32/LPR rows per pass, and
+// every warp keeps kDotUnroll passes of loads in flight.
+constexpr int kDotUnroll = 4;
 template <bool BF16>
 __global__ void fa_bwd_dot_kernel(const uint16_t* __restrict__ o, const uint16_t* __restrict__ dout,
                                   float* __restrict__ delta, int head_dim, int64_t rows_total, int seqlen_q,
                                   int heads, int64_t o_sb, int64_t o_ss, int64_t o_sh, int64_t do_sb, int64_t do_ss,
-                                  int64_t do_sh, int64_t d_sb, int64_t d_sh) {
+                                  int64_t do_sh, int64_t d_sb, int64_t d_sh, int lpr) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows_total) return;
-    // row enumerates (b, s, h) with h fastest: neighbouring warps read neighbouring heads of one token
-    const int h = (int)(row % heads);
-    const int64_t bs = row / heads;
-    const int s = (int)(bs % seqlen_q);
-    const int64_t b = bs / seqlen_q;
-    const uint16_t* po = o + b * o_sb + (int64_t)s * o_ss + (int64_t)h * o_sh;
-    const uint16_t* pd = dout + b * do_sb + (int64_t)s * do_ss + (int64_t)h * do_sh;
-    float acc = 0.f;
-    for (int c = lane * 8; c < head_dim; c += 256) {
-        const uint4 a = *reinterpret_cast<const uint4*>(po + c);
-        const uint4 g = *reinterpret_cast<const uint4*>(pd + c);
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+    const int rows_per_pass = 32 / lpr;
+    const int sub = lane / lpr, chunk = lane - sub * lpr;
+    const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t row0 = warp_id * (rows_per_pass * kDotUnroll) + sub;
+    uint4 a[kDotUnroll], g[kDotUnroll];
+    int64_t out_idx[kDotUnroll];
+    // row enumerates (b, s, h) with h fastest: neighbouring rows are neighbouring heads of one token. One 32-bit
+    // decomposition per thread, then carries (64-bit divisions per row made this kernel ALU-bound).
+    const uint32_t r32 = (uint32_t)(row0 < rows_total ? row0 : 0);
+    int h = (int)(r32 % (uint32_t)heads);
+    const uint32_t bs = r32 / (uint32_t)heads;
+    int sq = (int)(bs % (uint32_t)seqlen_q);
+    int64_t b = bs / (uint32_t)seqlen_q;
+#pragma unroll
+    for (int u = 0; u < kDotUnroll; ++u) {
+        const int64_t row = row0 + (int64_t)u * rows_per_pass;
+        a[u] = make_uint4(0, 0, 0, 0);
+        g[u] = make_uint4(0, 0, 0, 0);
+        out_idx[u] = -1;
+        if (row < rows_total) {
+            out_idx[u] = b * d_sb + (int64_t)h * d_sh + sq;
+            if (chunk * 8 < head_dim) {
+                a[u] = *reinterpret_cast<const uint4*>(o + b * o_sb + (int64_t)sq * o_ss + (int64_t)h * o_sh + chunk * 8);
+                g[u] = *reinterpret_cast<const uint4*>(dout + b * do_sb + (int64_t)sq * do_ss + (int64_t)h * do_sh + chunk * 8);
+            }
+        }
+        h += rows_per_pass;
+        while (h >= heads) {
+            h -= heads;
+            if (++sq == seqlen_q) {
+                sq = 0;
+                ++b;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kDotUnroll; ++u) {
+        const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, gw[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+        float acc = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float2 x, y;
@@ -169,10 +197,9 @@ __global__ void fa_bwd_dot_kernel(const uint16_t* __restrict__ o, const uint16_t
             acc = fmaf(x.x, y.x, acc);
             acc = fmaf(x.y, y.y, acc);
         }
+        for (int off = lpr >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (chunk == 0 && out_idx[u] >= 0) delta[out_idx[u]] = acc;
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) delta[b * d_sb + (int64_t)h * d_sh + s] = acc;
 }
 
 template <int D, bool BF16, bool FEAT, bool KV_STAT, bool DROPOUT>
@@ -244,7 +271,16 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
     auto bar_ring_empty = [&](int i) { return bars + 8 * (2 + RING + i); };
     constexpr int kB0 = 2 + 2 * RING;
     const uint32_t bar_t1_full = bars + 8 * (kB0 + 0);   // MMA -> element-wise: T1 ready
-    const uint32_t bar_t2_full = bars + 8 * (kB0 + 1);   // MMA -> element-wise: T2 ready
+    // MMA -> element-wise: T2 ready. The dQ pass has the out2 columns of TMEM to spare and keeps two T2 buffers
+    // (tile t uses buffer t & 1), so dP of the next tile is computed while this tile's dS is still being made:
+    // one barrier per buffer, because a barrier must never run two phases ahead of its waiter.
+    // Only where the ring is deep enough (head_dim <= 64): the early dP GEMM needs B2(t+1) resident while B1(t), B2(t)
+    // are still held, and with 5 slots (head_dim 128) waiting for it delays out1(t) and the slot releases behind it
+    // (measured: -5 % at head_dim 128, +18 % at head_dim 64).
+    constexpr bool T2DB = !KV_STAT && RING >= 6;
+    auto bar_t2_full = [&](int t) { return bars + 8 * (T2DB && (t & 1) ? kB0 + 5 : kB0 + 1); };
+    auto t2_parity = [&](int t) -> uint32_t { return T2DB ? (t >> 1) & 1 : t & 1; };
+    auto t2_col = [&](int t) { return T2DB && (t & 1) ? Cfg::kTmemOut2 : Cfg::kTmemT2; };
     const uint32_t bar_p_ready = bars + 8 * (kB0 + 2);   // element-wise -> MMA: T1 consumed (and P written)
     const uint32_t bar_ds_ready = bars + 8 * (kB0 + 3);  // element-wise -> MMA: dS written over T2
     const uint32_t bar_out_full = bars + 8 * (kB0 + 4);  // MMA -> epilogue: accumulators final
@@ -259,7 +295,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
             mbar_init(bar_ring_empty(i), 1);
         }
         mbar_init(bar_t1_full, 1);
-        mbar_init(bar_t2_full, 1);
+        mbar_init(bars + 8 * (kB0 + 1), 1);
+        mbar_init(bars + 8 * (kB0 + 5), 1);
         mbar_init(bar_p_ready, 8);
         mbar_init(bar_ds_ready, 8);
         mbar_init(bar_out_full, 1);
@@ -353,7 +390,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
             wait_full(1);
             tc_fence_after();
             issue_t(tT2, 1, 1);
-            umma_commit_elect(bar_t2_full);
+            umma_commit_elect(bar_t2_full(0));
             for (int t = 0; t < n_tiles; ++t) {
                 const uint32_t ph = t & 1;
                 mbar_wait(bar_p_ready, ph);  // T1(t) is in registers; in the dK/dV pass P(t) sits in T1's columns
@@ -365,17 +402,23 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
                     tc_fence_after();
                     issue_t(tT1, 0, 2 * t + 2);
                     umma_commit_elect(bar_t1_full);
+                    if constexpr (T2DB) {  // dP(t+1) goes into the other T2 buffer right away
+                        wait_full(2 * t + 3);
+                        tc_fence_after();
+                        issue_t(tmem_base + t2_col(t + 1), 1, 2 * t + 3);
+                        umma_commit_elect(bar_t2_full(t + 1));
+                    }
                 }
                 mbar_wait(bar_ds_ready, ph);
                 tc_fence_after();
-                issue_o(tO1, tT2, 2 * t, t > 0 ? 1u : 0u);
+                issue_o(tO1, tmem_base + t2_col(t), 2 * t, t > 0 ? 1u : 0u);
                 umma_commit_elect(bar_ring_empty((2 * t) % RING));
                 umma_commit_elect(bar_ring_empty((2 * t + 1) % RING));
-                if (t + 1 < n_tiles) {
+                if (!T2DB && t + 1 < n_tiles) {
                     wait_full(2 * t + 3);
                     tc_fence_after();
                     issue_t(tT2, 1, 2 * t + 3);
-                    umma_commit_elect(bar_t2_full);
+                    umma_commit_elect(bar_t2_full(t + 1));
                 }
             }
             umma_commit_elect(bar_out_full);
@@ -387,7 +430,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
         const int r = (warp & 3) * 32 + lane;      // row of the stationary block == TMEM lane
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tT1 = tmem_base + lane_off + Cfg::kTmemT1 + wg * CW;
-        const uint32_t tT2 = tmem_base + lane_off + Cfg::kTmemT2 + wg * CW;
+        const uint32_t tT2_0 = tmem_base + lane_off + wg * CW;  // + t2_col(t)
         const int x = x0 + r;  // this thread's query position (dQ pass) or key position (dK/dV pass)
         const float sl2 = FEAT ? 1.0f : p.scale_log2;
 
@@ -556,8 +599,9 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
             }
 
             // ---- T2 -> dS = P * (keep * rp * dP - delta)       (reference include/softmax.h:293-294)
-            mbar_wait(bar_t2_full, t & 1);
+            mbar_wait(bar_t2_full(t), t2_parity(t));
             tc_fence_after();
+            const uint32_t tT2 = tT2_0 + t2_col(t);
             uint32_t dsk[CW / 2];
 #pragma unroll
             for (int hc = 0; hc < CW / 32; ++hc) {

@@ -751,18 +751,21 @@ int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
     // 1. delta = rowsum(dO * O)   (reference include/product.h; returned as softmax_d)
     {
         const int64_t rows = (int64_t)nb * rows_q * p->num_heads;
+        int lpr = 1;  // lanes per row: head_dim / 8 rounded up to a power of two
+        while (lpr * 8 < p->head_dim) lpr <<= 1;
         const int warps = 8;
-        const dim3 grid((unsigned)((rows + warps - 1) / warps));
+        const int64_t rows_per_block = (int64_t)warps * (32 / lpr) * fa::kDotUnroll;
+        const dim3 grid((unsigned)((rows + rows_per_block - 1) / rows_per_block));
         const uint16_t* o = static_cast<const uint16_t*>(p->out);
         const uint16_t* d = static_cast<const uint16_t*>(p->dout);
         if (bf16)
             fa::fa_bwd_dot_kernel<true><<<grid, warps * 32, 0, stream>>>(o, d, p->softmax_d, p->head_dim, rows, (int)rows_q, p->num_heads,
                 varlen ? 0 : p->o_stride_b, p->o_stride_s, p->o_stride_h, varlen ? 0 : p->do_stride_b, p->do_stride_s, p->do_stride_h,
-                kp.lse_stride_b, kp.lse_stride_h);
+                kp.lse_stride_b, kp.lse_stride_h, lpr);
         else
             fa::fa_bwd_dot_kernel<false><<<grid, warps * 32, 0, stream>>>(o, d, p->softmax_d, p->head_dim, rows, (int)rows_q, p->num_heads,
                 varlen ? 0 : p->o_stride_b, p->o_stride_s, p->o_stride_h, varlen ? 0 : p->do_stride_b, p->do_stride_s, p->do_stride_h,
-                kp.lse_stride_b, kp.lse_stride_h);
+                kp.lse_stride_b, kp.lse_stride_h, lpr);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "fa_bwd_dot_kernel launch");

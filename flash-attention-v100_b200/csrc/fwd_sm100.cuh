@@ -130,6 +130,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; O is rescaled only whe
 #ifndef FA_SPLIT_P
 #define FA_SPLIT_P 1     // signal the MMA warp after 3/4 of P so P V starts before the last quarter
 #endif
+#ifndef FA_EARLY_QK
+#define FA_EARLY_QK 1    // head_dim <= 64: issue the left half of the next S = Q K^T as soon as the softmax warps
+#endif                   // hold S in registers (see kEarlyQK)
 
 // Optional event trace (build with -DFA_TRACE): lane 0 of every warp of CTA 0 appends (event, clock64)
 // pairs to a global buffer set through fa_b200_debug_set_trace(); tools/trace_timeline.py prints the
@@ -162,7 +165,7 @@ struct FwdConfig {
     static constexpr int kKvStages = (D == 256) ? 2 : (D == 128) ? 4 : 6;
     static constexpr int kSmemQ = kSplitD ? kTileBytes : 2 * kTileBytes;
     static constexpr int kSmemKV = kKvStages * kTileBytes;
-    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1;
+    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1 + 2;
     static constexpr int kOffBars = kSmemQ + kSmemKV;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
     static constexpr int kOffScale = (kOffTmemPtr + 16 + 15) & ~15;
@@ -173,6 +176,10 @@ struct FwdConfig {
     static constexpr int kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
     static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + kDO;
     static constexpr int kTmemPOff = 64;
+    // Early left half of S: two N=64 MMAs read the Q tile from shared memory twice, and an SS-form 128x128x16 MMA
+    // already needs the full 128 B/clk of shared-memory bandwidth -- measured -10 % at head_dim 128 (tensor pipe is
+    // the bottleneck there), +7 % at head_dim 64 (the softmax is, and the pipe has slack).
+    static constexpr bool kEarlyQK = FA_EARLY_QK && (D == 64);
 };
 
 // Per-sequence geometry shared by every role.
@@ -353,7 +360,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     auto bar_sched_full = [&](int b) { return bars + 8 * (kB0 + 15 + b); };   // loader -> everyone: work id
     auto bar_sched_empty = [&](int b) { return bars + 8 * (kB0 + 17 + b); };  // everyone -> loader
     const uint32_t bar_vfix = bars + 8 * (kB0 + 19);  // sanitiser -> MMA: tail rows of the ragged V tile zeroed
-    static_assert(kB0 + 20 <= Cfg::kNumBars, "barrier table too small");
+    auto bar_s_loaded = [&](int s) { return bars + 8 * (kB0 + 20 + s); };  // softmax -> MMA: S_s is in registers
+    static_assert(kB0 + 22 <= Cfg::kNumBars, "barrier table too small");
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffTmemPtr);
     float* sScale = reinterpret_cast<float*>(sgen + Cfg::kOffScale);
     float* sRowSum = reinterpret_cast<float*>(sgen + Cfg::kOffRowSum);
@@ -368,6 +376,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             mbar_init(bar_stats(s), 4);
             mbar_init(bar_o_full(s), 1);
             mbar_init(bar_p_last(s), 4);
+            mbar_init(bar_s_loaded(s), 4);
             mbar_init(bar_final(s, 0), 4);
             mbar_init(bar_final(s, 1), 4);
             mbar_init(bar_sched_full(s), 1);
@@ -493,6 +502,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         // ============================================================ MMA issuer
         reg_dec<48>();
         constexpr uint32_t idesc_qk = umma_idesc_f16(BF16, BM, BN, false, false);
+        constexpr uint32_t idesc_qk_half = umma_idesc_f16(BF16, BM, BN / 2, false, false);
         constexpr uint32_t idesc_pv = umma_idesc_f16(BF16, BM, DO, false, true);
         const uint32_t tS[2] = {tmem_base + Cfg::kTmemS0, tmem_base + Cfg::kTmemS1};
         const uint32_t tO[2] = {tmem_base + Cfg::kTmemO0, tmem_base + Cfg::kTmemO1};
@@ -510,6 +520,16 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             if constexpr (D == 256) umma_issue_qk_d256(tS[s], a_lo, b_lo, kDescHi, kDescHi, idesc_qk);
             else if constexpr (D == 128) umma_issue_qk_d128(tS[s], a_lo, b_lo, kDescHi, kDescHi, idesc_qk);
             else umma_issue_qk_d64(tS[s], a_lo, b_lo, kDescHi, kDescHi, idesc_qk);
+        };
+        // One half of S_s = Q_s K^T: keys [64 h, 64 h + 64) of the tile -> columns [64 h, 64 h + 64) of S_s. The left
+        // half does not touch the columns P_s lives in, so it can run while the previous P_s is still being made.
+        auto issue_qk_half = [&](int s, uint32_t k_smem, int h) {
+            const uint32_t a_lo = lo_addr(sQ + (SPLIT ? 0 : s) * Cfg::kTileBytes) | kLoKmajor;
+            const uint32_t b_lo = lo_addr(k_smem + h * 64 * 128) | kLoKmajor;  // 64 rows x 128 B further in every block
+            const uint32_t d = tS[s] + h * 64;
+            if constexpr (D == 256) umma_issue_qk_d256(d, a_lo, b_lo, kDescHi, kDescHi, idesc_qk_half);
+            else if constexpr (D == 128) umma_issue_qk_d128(d, a_lo, b_lo, kDescHi, kDescHi, idesc_qk_half);
+            else umma_issue_qk_d64(d, a_lo, b_lo, kDescHi, kDescHi, idesc_qk_half);
         };
         auto slot_addr = [&](int r) { return sKV + (r % KV) * Cfg::kTileBytes; };
         auto wait_full = [&](int r) { mbar_wait(bar_kv_full(r % KV), (r / KV) & 1); };
@@ -542,6 +562,15 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         const uint32_t tP = tS[s] + Cfg::kTmemPOff;
                         // split-D: stage s multiplies by its own 128-column half of V (two swizzle blocks further)
                         const uint32_t v_lo = lo_addr(slot_addr(ring + 2 * it - 1) + (SPLIT ? s * 2 * Cfg::kHalfBytes : 0)) | kLoVmn;
+                        if (Cfg::kEarlyQK) {
+                            // S_s(j) sits in the softmax warps' registers: columns [0,64) of S_s are free, so the left
+                            // half of the next S_s can be computed while P_s(j) is still being made
+                            mbar_wait(bar_s_loaded(s), ph);
+                            if (do_qk) {
+                                tc_fence_after();
+                                issue_qk_half(s, slot_addr(ring + 2 * it), 0);
+                            }
+                        }
                         // P_s(j) written, O_s rescaled; for j == 0 this also means the correction warps
                         // finished reading O_s of the previous item (their arrival comes after that epilogue)
                         mbar_wait(bar_p_full(s), ph);
@@ -560,7 +589,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     }
                     if (do_qk) {
                         tc_fence_after();
-                        issue_qk(s, slot_addr(ring + 2 * it));
+                        if (Cfg::kEarlyQK && do_pv) issue_qk_half(s, slot_addr(ring + 2 * it), 1);  // left half went ahead
+                        else issue_qk(s, slot_addr(ring + 2 * it));
                         umma_commit_elect(bar_s_full(s));
                         FA_TRACE_EV(120 + s);  // MMA: QK_s issued
                     }
@@ -630,6 +660,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 float v[BN];
                 tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
                 FA_TRACE_EV(2);  // softmax: S in registers
+                if (Cfg::kEarlyQK) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_s_loaded(s));
+                }
 
                 if constexpr (FEAT) {
                     // reference order (include/mat_mul.h:111-117): scale, ALiBi, then softcap

@@ -54,9 +54,16 @@ FA_DEVICE bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// -DFA_DEADLOCK_TRAP=<polls>: bring-up builds trap instead of spinning forever on a barrier that never flips.
 FA_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef FA_DEADLOCK_TRAP
+    for (uint32_t polls = 0; !mbar_try_wait(bar, parity); ++polls) {
+        if (polls > (uint32_t)(FA_DEADLOCK_TRAP)) __trap();
+    }
+#else
     while (!mbar_try_wait(bar, parity)) {
     }
+#endif
 }
 
 // ---------------------------------------------------------------- proxies / fences
