@@ -77,6 +77,34 @@ def bench_case(name, B, S, H, Hk, D, dtype, causal, iters=10, window=(-1, -1)):
     results.append(rec)
 
 
+def bench_varlen(name, iters=20):
+    """BASELINE config 3: 64 packed sequences, randint(1, 2049) seed 0, H=32, D=128, bf16 causal."""
+    from flash_attn_v100 import flash_attn_varlen_func
+
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(1, 2049, (64,), generator=g)
+    H, D, T = 32, 128, int(lens.sum())
+    torch.manual_seed(421)
+    q = torch.randn(T, H, D, device="cuda", dtype=torch.bfloat16)
+    k, v = torch.randn_like(q), torch.randn_like(q)
+    cu = torch.nn.functional.pad(lens.cumsum(0), (1, 0)).int().cuda()
+    mx = int(lens.max())
+    for _ in range(3):
+        flash_attn_varlen_func(q, k, v, cu, cu, mx, mx, causal=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        flash_attn_varlen_func(q, k, v, cu, cu, mx, mx, causal=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 4 * D * H * float((lens.double() * (lens.double() + 1) / 2).sum())
+    rec = {"name": name, "ms": ms, "tflops": flops / ms / 1e9}
+    print(json.dumps(rec), flush=True)
+    results.append(rec)
+
+
 if __name__ == "__main__":
     f16, bf16 = torch.float16, torch.bfloat16
     t0 = time.time()
@@ -102,6 +130,7 @@ if __name__ == "__main__":
         bench_case("bf16_B4_H32_S16384_D128_causal", 4, 16384, 32, 32, 128, bf16, True, iters=5)
         bench_case("f16_B8_H32_S4096_D64_causal", 8, 4096, 32, 32, 64, f16, True)
         bench_case("C1_f16_B2_H8_S512_D64_full", 2, 512, 8, 8, 64, f16, False)
+        bench_varlen("C3_varlen_64seqs_H32_D128_causal")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(results, open(os.path.join(ROOT, "gpurun_out", f"quick_{tag}.json"), "w"), indent=1)
     print("elapsed", time.time() - t0)
