@@ -1,0 +1,87 @@
+"""CUDA-graph capture of the hot path: a serving loop replays one captured decode step (append + rotary +
+split-KV attention + combine) and a captured dense forward; replays must match eager calls on the same data.
+The library only enqueues kernels on the caller's stream (no allocation, no synchronisation after the first
+call on a device), which is what makes its calls capturable."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(fa_lib):
+    import flash_attn_v100 as m
+
+    return m
+
+
+def _rotary(seqlen, rot, dtype):
+    inv = 1.0 / (10000 ** (torch.arange(0, rot, 2, dtype=torch.float32) / rot))
+    ang = torch.outer(torch.arange(seqlen, dtype=torch.float32), inv)
+    return ang.cos().to(dtype).cuda(), ang.sin().to(dtype).cuda()
+
+
+def test_decode_step_replays_from_a_cuda_graph(api):
+    torch.manual_seed(11)
+    dt = torch.bfloat16
+    B, H, Hk, D, cap, page = 4, 16, 4, 128, 2048, 256
+    n_pages = B * (cap // page)
+    kc = torch.randn(n_pages, page, Hk, D, device="cuda", dtype=dt)
+    vc = torch.randn(n_pages, page, Hk, D, device="cuda", dtype=dt)
+    bt = torch.randperm(n_pages, generator=torch.Generator().manual_seed(0)).view(B, -1).int().cuda()
+    lens = torch.tensor([100, 1500, 7, 2000], dtype=torch.int32, device="cuda")
+    q = torch.randn(B, 1, H, D, device="cuda", dtype=dt)
+    kn = torch.randn(B, 1, Hk, D, device="cuda", dtype=dt)
+    vn = torch.randn(B, 1, Hk, D, device="cuda", dtype=dt)
+    cos, sin = _rotary(cap, D, dt)
+
+    def step(kc_, vc_):
+        return api.flash_attn_with_kvcache(q, kc_, vc_, kn, vn, rotary_cos=cos, rotary_sin=sin, cache_seqlens=lens,
+                                           block_table=bt, causal=True, rotary_interleaved=False)
+
+    step(kc.clone(), vc.clone())  # first call on the device: one-time set-up must not happen inside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            out_static = step(kc, vc)
+    torch.cuda.current_stream().wait_stream(side)
+
+    for it in range(3):  # three decode steps: new token, lengths advance, all through device memory only
+        q.copy_(torch.randn_like(q))
+        kn.copy_(torch.randn_like(kn))
+        vn.copy_(torch.randn_like(vn))
+        kc_ref, vc_ref = kc.clone(), vc.clone()
+        ref = step(kc_ref, vc_ref)  # eager, on a copy of the cache as it is before this step
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out_static, ref), f"replay {it} differs from the eager call"
+        assert torch.equal(kc, kc_ref) and torch.equal(vc, vc_ref), "the replay must append exactly like the eager call"
+        lens.add_(1)
+
+
+def test_dense_forward_replays_from_a_cuda_graph(api):
+    torch.manual_seed(12)
+    q = torch.randn(2, 700, 8, 128, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(2, 700, 2, 128, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(2, 700, 2, 128, device="cuda", dtype=torch.bfloat16)
+    api.flash_attn_func(q, k, v, causal=True)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out_static = api.flash_attn_func(q, k, v, causal=True)
+    for _ in range(3):
+        q.copy_(torch.randn_like(q))
+        k.copy_(torch.randn_like(k))
+        g.replay()
+        ref = api.flash_attn_func(q, k, v, causal=True)
+        torch.cuda.synchronize()
+        assert torch.equal(out_static, ref)
