@@ -289,7 +289,11 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
     kern_ms = statistics.mean(per_launch_ms)
     achieved = flops_rank / (kern_ms * 1e-3) / 1e12
     threads = os.cpu_count() or 1
-    cpu_tf, cpu_dt, cpu_kind, cpu_sample = cpu_reference_sample(w, threads)
+    cpu_baseline = None  # timed on rank 0 at N=1 only (the scaling runs would repeat the same CPU work)
+    if world == 1:
+        cpu_tf, cpu_dt, cpu_kind, cpu_sample = cpu_reference_sample(w, threads)
+        cpu_baseline = {"value": cpu_tf, "unit": UNIT, "cores": threads, "kind": cpu_kind, "sample": cpu_sample,
+                        "sample_seconds": cpu_dt}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tpath):
@@ -306,8 +310,7 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
                      "traffic": traffic, "peak_source": f"{peak_src} bf16 burst (MEASURED_PEAKS.json)",
                      "frac_of_sustained": achieved / peak_sustained, "frac_of_nominal_2250": achieved / 2250.0,
                      "kernel": "fa_fwd_sm100_kernel<128,bf16>", "kernel_ms": kern_ms},
-        "cpu_baseline": {"value": cpu_tf, "unit": UNIT, "cores": threads, "kind": cpu_kind, "sample": cpu_sample,
-                         "sample_seconds": cpu_dt},
+        "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "pinned host q,k,v -> H2D, kernel, out -> D2H, pipelined per batch element on 2 streams"},
         "gpu_launches": launches,
