@@ -182,7 +182,7 @@ def run_reference(args, w, rank: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -316,12 +316,26 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_OUT = sys.stdout
+
+
+def _reserve_stdout_for_the_json_line():
+    """stdout must carry exactly one JSON line, but native libraries write there too (NCCL prints its version banner on
+    stdout whatever NCCL_DEBUG is set to after import). Keep a private handle on the real stdout for the JSON line
+    and point file descriptor 1 at stderr for everything else."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    _reserve_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
