@@ -116,7 +116,7 @@ def test_softcap_and_alibi(api, softcap, alibi, causal, D):
 
 
 @pytest.mark.parametrize("D", [16, 32, 40, 80, 96, 100, 136, 192, 250, 256])
-def test_head_dims_by_padding(api, D):
+def test_head_dims_any_multiple_of_8(api, D):
     q, k, v = rand_qkv(1, 200, 264, 4, 4, D, torch.float16)
     out = api.flash_attn_func(q, k, v, causal=True)
     assert out.shape == q.shape
