@@ -82,8 +82,15 @@ struct alignas(64) BwdKernelParams {
     uint32_t drop_thr;
     uint64_t drop_seed;
     uint64_t drop_offset;
-    int num_blocks;  // stationary blocks along the sequence (grid.x)
+    int num_blocks;  // stationary blocks along the (longest) sequence
     int reverse;     // launch the last block first (dQ pass with a causal / right-window mask)
+    // 1-D launch order: CTA w = (block rank, (head, batch) pair[, D-half]), numbered section by section -- a section is
+    // `section_bh` (head, batch) pairs whose streamed tensors fit L2 together; inside a section every pair's
+    // first-ranked (longest) block comes first. The hardware dispatches CTAs in this order, so the long blocks of a
+    // section start first (with GQA the dK/dV blocks differ by up to 128 tiles) and the section's streams stay in L2.
+    int num_bh;       // (grid heads) x batch; grid heads = KV heads in the dK/dV pass, query heads in the dQ pass
+    int grid_heads;
+    int section_bh;
 };
 
 template <int D>
@@ -213,7 +220,17 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
     constexpr int RING = Cfg::kRing;
 
     // ------------------------------------------------------------------ geometry (uniform over the CTA)
-    const int batch = blockIdx.z;
+    int w = (int)blockIdx.x;
+    const int dhalf = SPLIT ? w & 1 : 0;  // split-D: which 128-column half of the outputs is mine
+    if constexpr (SPLIT) w >>= 1;
+    const int per_section = p.section_bh * p.num_blocks;
+    const int sec = w / per_section;
+    const int w_in = w - sec * per_section;
+    const int sec_n = min(p.section_bh, p.num_bh - sec * p.section_bh);
+    const int rank = w_in / sec_n;
+    const int bh = sec * p.section_bh + (w_in - rank * sec_n);
+    const int hh = bh % p.grid_heads;  // KV head (dK/dV pass) or query head (dQ pass)
+    const int batch = bh / p.grid_heads;
     int q_off = 0, q_b = batch, seqlen_q = p.seqlen_q, k_off = 0, k_b = batch, seqlen_k = p.seqlen_k;
     if (p.cu_seqlens_q) {
         q_off = p.cu_seqlens_q[batch];
@@ -226,13 +243,11 @@ fa_bwd_sm100_kernel(const __grid_constant__ BwdKernelParams p) {
     const int o_b = p.cu_seqlens_q ? 0 : batch;
     const int G = p.heads_per_kv;
     const int off = seqlen_k - seqlen_q;
-    const int bx = SPLIT ? (int)blockIdx.x >> 1 : (int)blockIdx.x;
-    const int dhalf = SPLIT ? (int)blockIdx.x & 1 : 0;  // split-D: which 128-column half of the outputs is mine
-    const int blk = p.reverse ? p.num_blocks - 1 - bx : bx;
+    const int blk = p.reverse ? p.num_blocks - 1 - rank : rank;
     const int x0 = blk * BT;  // first row of the stationary block (query position or key position)
     if (x0 >= (KV_STAT ? seqlen_k : seqlen_q)) return;
-    const int kv_head = KV_STAT ? (int)blockIdx.y : (int)blockIdx.y / G;
-    const int head0 = KV_STAT ? kv_head * G : (int)blockIdx.y;  // first (dK/dV pass) or only (dQ pass) query head
+    const int kv_head = KV_STAT ? hh : hh / G;
+    const int head0 = KV_STAT ? kv_head * G : hh;  // first (dK/dV pass) or only (dQ pass) query head
 
     // streamed tiles [t_lo, t_hi) along the other sequence, visible to at least one row of this block
     int t_lo = 0, t_hi;

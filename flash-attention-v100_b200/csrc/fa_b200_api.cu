@@ -770,16 +770,33 @@ int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "fa_bwd_dot_kernel launch");
     }
+    // 1-D grid in sectioned longest-first order (BwdKernelParams::section_bh): a section is the (head, batch) pairs
+    // whose two streamed tensors (`stream_rows` rows per grid head) fit ~32 MB of L2.
+    // Sections wider than one pair only pay where block lengths differ a lot: the dK/dV pass with GQA, whose blocks
+    // stream the whole group (measured: +4.5 % there, -1.5..-3.5 % on uniform work from the lost L2 sharing between
+    // the blocks of one head). `wide = false` is the plain order: all blocks of a pair, then the next pair.
+    auto set_order = [&](int blocks, int grid_heads, int64_t stream_rows_per_head, bool wide) {
+        kp.num_blocks = blocks;
+        kp.grid_heads = grid_heads;
+        kp.num_bh = grid_heads * p->batch;
+        const int64_t bytes = 2ll * stream_rows_per_head * p->head_dim * 2;
+        int64_t sec = (32ll << 20) / (bytes > 0 ? bytes : 1);
+        if (sec < 1 || !wide) sec = 1;
+        if (sec > kp.num_bh) sec = kp.num_bh;
+        kp.section_bh = (int)sec;
+        return dim3((unsigned)((int64_t)blocks * kp.num_bh * (split_d ? 2 : 1)), 1, 1);
+    };
+    CHECK_ARG(((int64_t)(p->seqlen_k + 127) / 128 + (p->seqlen_q + 127) / 128) * p->batch * p->num_heads * 2 < (1ll << 31),
+              "too many (block, head, batch) work items for one launch");
     // 2. dK / dV pass: one CTA per (128-key block, KV head, batch)
     {
-        kp.num_blocks = (p->seqlen_k + 127) / 128;
         kp.reverse = 0;
-        dim3 grid(kp.num_blocks * (split_d ? 2 : 1), p->num_heads_k, p->batch);
+        dim3 grid = set_order((p->seqlen_k + 127) / 128, p->num_heads_k, (int64_t)p->seqlen_q * kp.heads_per_kv,
+                              kp.heads_per_kv > 1 && (wl >= 0 || wr >= 0));
         if (int rc = launch_bwd<true>(kp, p->head_dim, bf16, feat, dropout, grid, stream)) return rc;
     }
     // 3. dQ pass: one CTA per (128-query block, head, batch)
     {
-        kp.num_blocks = (p->seqlen_q + 127) / 128;
         kp.reverse = wr >= 0 ? 1 : 0;
         if (split_d) {  // dQ pass: Q, dO stationary (128-row boxes); K, V streamed in 64-row tiles
             if (int rc = map_q(&kp.tm_q_stat, 128)) return rc;
@@ -787,7 +804,7 @@ int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
             if (int rc = map_k(&kp.tm_k, stream_rows)) return rc;
             if (int rc = map_v(&kp.tm_v, stream_rows)) return rc;
         }
-        dim3 grid(kp.num_blocks * (split_d ? 2 : 1), p->num_heads, p->batch);
+        dim3 grid = set_order((p->seqlen_q + 127) / 128, p->num_heads, p->seqlen_k, false);
         if (int rc = launch_bwd<false>(kp, p->head_dim, bf16, feat, dropout, grid, stream)) return rc;
     }
     return 0;
