@@ -269,13 +269,18 @@ dim3 set_launch_order(fa::FwdKernelParams& kp, int device, int batch, int heads,
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
+    // cudaSetDevice is called even when `dev` is already the current device: on a thread that has not touched CUDA
+    // yet (PyTorch's autograd thread calling the backward) it is what binds the primary context to the thread, and
+    // cuTensorMapEncodeTiled is a driver call that fails with CUDA_ERROR_INVALID_CONTEXT without one.
     explicit DeviceGuard(int dev) {
         if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
-        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        if (ok && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        if (ok) target = dev;
     }
     ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
+        if (prev >= 0 && prev != target) cudaSetDevice(prev);
     }
+    int target = -1;
 };
 
 int check_common(const fa_b200_params_t* p) {

@@ -267,3 +267,33 @@ def test_config2_geometry_backward_sampled(api):
         dv_ref[:, hk] += p[:, S - n:].T @ dof[0, S - n:, h]
     assert (dk[0, S - n:].double().cpu() - dk_ref).abs().max().item() <= 4e-2 * max(1.0, dk_ref.abs().max().item())
     assert (dv[0, S - n:].double().cpu() - dv_ref).abs().max().item() <= 4e-2 * max(1.0, dv_ref.abs().max().item())
+
+
+def test_backward_called_first_from_a_fresh_thread(op):
+    """PyTorch runs backward() on its own autograd thread, which may not have touched CUDA before our call:
+    the C layer must bind the device's context itself (cuTensorMapEncodeTiled is a driver call)."""
+    import threading
+
+    torch.manual_seed(5)
+    q = torch.randn(1, 2, 130, 64, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(1, 2, 200, 64, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn_like(k)
+    do = torch.randn_like(q)
+    out, lse, _, rng = op.fwd(q, k, v, None, None, 0.0, 0.125, True, -1, -1, 0.0, False, None)
+    expect = op.bwd(do, q, k, v, out, lse, None, None, None, None, 0.0, 0.125, True, -1, -1, 0.0, False, None, rng)
+    torch.cuda.synchronize()
+    box = {}
+
+    def work():
+        try:
+            box["res"] = op.bwd(do, q, k, v, out, lse, None, None, None, None, 0.0, 0.125, True, -1, -1, 0.0, False, None, rng)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            box["err"] = e
+
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    assert "err" not in box, box.get("err")
+    for a, b in zip(box["res"][:3], expect[:3]):
+        assert torch.equal(a, b)

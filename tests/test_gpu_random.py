@@ -25,11 +25,11 @@ def _tol(dtype):
     return 2e-2 if dtype == torch.bfloat16 else 4e-3
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(40))
 def test_random_dense(api, seed):
     rng = random.Random(seed)
     dtype = rng.choice([torch.float16, torch.bfloat16])
-    D = rng.choice([64, 128, 32, 96])
+    D = rng.choice([64, 128, 32, 96, 256, 16, 192])
     Hk = rng.choice([1, 2, 3])
     H = Hk * rng.choice([1, 2, 4])
     B = rng.randint(1, 3)
@@ -50,11 +50,11 @@ def test_random_dense(api, seed):
     assert torch.isfinite(out.float()).all() and err <= _tol(dtype), (seed, err)
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(16))
 def test_random_varlen(api, seed):
     rng = random.Random(1000 + seed)
     dtype = rng.choice([torch.float16, torch.bfloat16])
-    D = rng.choice([64, 128])
+    D = rng.choice([64, 128, 256, 40])
     Hk = rng.choice([1, 2])
     H = Hk * rng.choice([1, 4])
     nseq = rng.randint(1, 9)
@@ -74,11 +74,11 @@ def test_random_varlen(api, seed):
     assert torch.isfinite(out.float()).all() and err <= _tol(dtype), (seed, err)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(14))
 def test_random_kvcache(api, seed):
     rng = random.Random(2000 + seed)
     dtype = rng.choice([torch.float16, torch.bfloat16])
-    D = rng.choice([64, 128])
+    D = rng.choice([64, 128, 256, 32])
     Hk = rng.choice([1, 2, 4])
     H = Hk * rng.choice([1, 2, 8])
     B = rng.randint(1, 4)
@@ -107,3 +107,43 @@ def test_random_kvcache(api, seed):
     err = (out.double().cpu() - ref).abs().max().item()
     assert torch.isfinite(out.float()).all() and err <= _tol(dtype), (seed, err)
     assert (lse.double().cpu() - lse_ref).abs().max().item() < 3e-3
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_backward(api, seed):
+    """dQ, dK, dV through autograd against the float64 oracle: head dims of all three tile widths, GQA, ragged
+    lengths, masks, softcap, dropout (the oracle replays the forward's Philox stream from the generator state)."""
+    rng = random.Random(3000 + seed)
+    dtype = rng.choice([torch.float16, torch.bfloat16])
+    D = rng.choice([64, 128, 256, 32, 96, 192])
+    Hk = rng.choice([1, 2])
+    H = Hk * rng.choice([1, 2, 4])
+    B = rng.randint(1, 2)
+    Sq = rng.choice([1, 64, 128, 129, 200, 256, 300, 513])
+    Sk = rng.choice([8, 128, 136, 256, 384, 520])
+    kw = {}
+    if rng.random() < 0.5:
+        kw["causal"] = True
+    elif rng.random() < 0.4:
+        kw["window_size"] = (rng.randint(0, 200), rng.randint(0, 100))
+    p_drop = rng.choice([0.0, 0.0, 0.2])
+    if p_drop == 0.0 and rng.random() < 0.25:
+        kw["softcap"] = 20.0
+    torch.manual_seed(seed)
+    q = torch.randn(B, Sq, H, D, device="cuda", dtype=dtype, requires_grad=True)
+    k = torch.randn(B, Sk, Hk, D, device="cuda", dtype=dtype, requires_grad=True)
+    v = torch.randn(B, Sk, Hk, D, device="cuda", dtype=dtype, requires_grad=True)
+    do = torch.randn(B, Sq, H, D, device="cuda", dtype=dtype)
+    okw = dict(kw)
+    if p_drop > 0.0:
+        gen = torch.cuda.default_generators[0]
+        gen.manual_seed(500 + seed)
+        okw["rng_state"] = (gen.initial_seed(), gen.get_offset())
+        kw["dropout_p"] = okw["dropout_p"] = p_drop
+    out = api.flash_attn_func(q, k, v, **kw)
+    dq, dk, dv = torch.autograd.grad(out, (q, k, v), do)
+    rq, rk, rv, _ = ao.flash_attn_bwd_ref(do, q, k, v, **okw)
+    tol = (4e-2 if dtype == torch.bfloat16 else 6e-3) / (1.0 - p_drop)
+    for name, got, ref in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        err = (got.double().cpu() - ref).abs().max().item()
+        assert torch.isfinite(got.float()).all() and err <= tol * max(1.0, ref.abs().max().item()), (seed, name, err)
