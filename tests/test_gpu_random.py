@@ -4,6 +4,7 @@ Seeds are fixed, so failures reproduce; sizes are small enough for the float64 o
 Exercises the persistent scheduler with many work items of different lengths in one launch (ragged varlen
 batches, skipped blocks, empty key ranges) -- the situations the hand-picked cases may miss.
 """
+import os
 import random
 
 import pytest
@@ -12,6 +13,9 @@ import torch
 from oracle import attention_oracle as ao
 
 pytestmark = pytest.mark.gpu
+
+# FA_FUZZ_MULT=k runs k times as many seeds per sweep (a longer fuzzing session on the GPU box; default 1)
+_MULT = int(os.environ.get("FA_FUZZ_MULT", "1"))
 
 
 @pytest.fixture(scope="module")
@@ -25,7 +29,7 @@ def _tol(dtype):
     return 2e-2 if dtype == torch.bfloat16 else 4e-3
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(40 * _MULT))
 def test_random_dense(api, seed):
     rng = random.Random(seed)
     dtype = rng.choice([torch.float16, torch.bfloat16])
@@ -50,7 +54,7 @@ def test_random_dense(api, seed):
     assert torch.isfinite(out.float()).all() and err <= _tol(dtype), (seed, err)
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(16 * _MULT))
 def test_random_varlen(api, seed):
     rng = random.Random(1000 + seed)
     dtype = rng.choice([torch.float16, torch.bfloat16])
@@ -74,7 +78,7 @@ def test_random_varlen(api, seed):
     assert torch.isfinite(out.float()).all() and err <= _tol(dtype), (seed, err)
 
 
-@pytest.mark.parametrize("seed", range(14))
+@pytest.mark.parametrize("seed", range(14 * _MULT))
 def test_random_kvcache(api, seed):
     rng = random.Random(2000 + seed)
     dtype = rng.choice([torch.float16, torch.bfloat16])
@@ -109,7 +113,7 @@ def test_random_kvcache(api, seed):
     assert (lse.double().cpu() - lse_ref).abs().max().item() < 3e-3
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(24 * _MULT))
 def test_random_backward(api, seed):
     """dQ, dK, dV through autograd against the float64 oracle: head dims of all three tile widths, GQA, ragged
     lengths, masks, softcap, dropout (the oracle replays the forward's Philox stream from the generator state)."""
@@ -144,6 +148,40 @@ def test_random_backward(api, seed):
     dq, dk, dv = torch.autograd.grad(out, (q, k, v), do)
     rq, rk, rv, _ = ao.flash_attn_bwd_ref(do, q, k, v, **okw)
     tol = (4e-2 if dtype == torch.bfloat16 else 6e-3) / (1.0 - p_drop)
+    for name, got, ref in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        err = (got.double().cpu() - ref).abs().max().item()
+        assert torch.isfinite(got.float()).all() and err <= tol * max(1.0, ref.abs().max().item()), (seed, name, err)
+
+
+@pytest.mark.parametrize("seed", range(12 * _MULT))
+def test_random_varlen_backward(api, seed):
+    rng = random.Random(4000 + seed)
+    dtype = rng.choice([torch.float16, torch.bfloat16])
+    D = rng.choice([64, 128, 256, 48])
+    Hk = rng.choice([1, 2])
+    H = Hk * rng.choice([1, 2])
+    nseq = rng.randint(1, 6)
+    lq = [rng.choice([1, 5, 64, 128, 130, 257, 400]) for _ in range(nseq)]
+    lk = lq if rng.random() < 0.6 else [rng.choice([8, 24, 128, 136, 392]) for _ in range(nseq)]
+    kw = {}
+    if rng.random() < 0.6:
+        kw["causal"] = True
+    elif rng.random() < 0.5:
+        kw["window_size"] = (rng.randint(0, 150), rng.randint(0, 60))
+    use_alibi = rng.random() < 0.25
+    torch.manual_seed(seed)
+    q = torch.randn(sum(lq), H, D, device="cuda", dtype=dtype, requires_grad=True)
+    k = torch.randn(sum(lk), Hk, D, device="cuda", dtype=dtype, requires_grad=True)
+    v = torch.randn(sum(lk), Hk, D, device="cuda", dtype=dtype, requires_grad=True)
+    do = torch.randn(sum(lq), H, D, device="cuda", dtype=dtype)
+    if use_alibi:
+        kw["alibi_slopes"] = (torch.rand(H, device="cuda") * 0.2).float()
+    cq = torch.tensor([0] + list(torch.tensor(lq).cumsum(0)), dtype=torch.int32, device="cuda")
+    ck = torch.tensor([0] + list(torch.tensor(lk).cumsum(0)), dtype=torch.int32, device="cuda")
+    out = api.flash_attn_varlen_func(q, k, v, cq, ck, max(lq), max(lk), **kw)
+    dq, dk, dv = torch.autograd.grad(out, (q, k, v), do)
+    rq, rk, rv, _ = ao.flash_attn_varlen_bwd_ref(do, q, k, v, cq, ck, max(lq), max(lk), **kw)
+    tol = 4e-2 if dtype == torch.bfloat16 else 6e-3
     for name, got, ref in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
         err = (got.double().cpu() - ref).abs().max().item()
         assert torch.isfinite(got.float()).all() and err <= tol * max(1.0, ref.abs().max().item()), (seed, name, err)
