@@ -160,6 +160,39 @@ def cpu_reference_sample(w, threads: int):
     return flops / dt / 1e12, dt, kind, f"{heads} of {w['batch'] * w['heads']} (batch,head) problems of the workload, one per host thread"
 
 
+def cpu_sdpa_sample(w, threads: int):
+    """The north star's named yardstick beside the reference's own loop: torch SDPA on the host cores, on one batch
+    element of the workload (all heads; bf16 inputs upcast to fp32 as the reference's test.py:18-34 does)."""
+    import torch
+    import torch.nn.functional as F
+
+    S, D, H, Hk = w["seqlen"], w["head_dim"], w["heads"], w["heads_k"]
+    torch.manual_seed(421)
+    q = torch.randn(1, H, S, D, dtype=torch.float32)
+    k = torch.randn(1, Hk, S, D, dtype=torch.float32)
+    v = torch.randn(1, Hk, S, D, dtype=torch.float32)
+    mask = None
+    if w["window"][0] >= 0:  # causal + left window as an explicit boolean mask
+        i = torch.arange(S)[:, None]
+        j = torch.arange(S)[None, :]
+        mask = (j <= i) & (j >= i - w["window"][0])
+    kwargs = dict(attn_mask=mask) if mask is not None else dict(is_causal=bool(w["causal"]))
+    if mask is not None:  # the masked path materialises the scores: keep the sample to one GQA group / 4 heads
+        g = H // Hk
+        hs = max(4 // g, 1) * g
+        q, k, v, H, Hk = q[:, :hs], k[:, :hs // g], v[:, :hs // g], hs, hs // g
+    if Hk != H:
+        kwargs["enable_gqa"] = True
+    torch.set_num_threads(threads)
+    F.scaled_dot_product_attention(q[:, :, :256], k[:, :, :256], v[:, :, :256], is_causal=True, **({"enable_gqa": True} if Hk != H else {}))
+    t0 = time.perf_counter()
+    F.scaled_dot_product_attention(q, k, v, **kwargs)
+    dt = time.perf_counter() - t0
+    flops = algorithmic_flops(dict(w, batch=1, heads=H))
+    return {"value": flops / dt / 1e12, "unit": UNIT, "cores": threads, "kind": "torch SDPA fp32 on the host",
+            "sample": f"1 of {w['batch']} batch elements of the workload, {H} of {w['heads']} heads", "sample_seconds": dt}
+
+
 def run_reference(args, w, rank: int):
     if rank != 0:
         return
@@ -294,6 +327,10 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
         cpu_tf, cpu_dt, cpu_kind, cpu_sample = cpu_reference_sample(w, threads)
         cpu_baseline = {"value": cpu_tf, "unit": UNIT, "cores": threads, "kind": cpu_kind, "sample": cpu_sample,
                         "sample_seconds": cpu_dt}
+        try:
+            cpu_baseline["torch_sdpa"] = cpu_sdpa_sample(w, threads)
+        except Exception as e:  # noqa: BLE001  (an extra yardstick must never cost the bench line)
+            cpu_baseline["torch_sdpa"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tpath):
