@@ -185,3 +185,26 @@ def test_random_varlen_backward(api, seed):
     for name, got, ref in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
         err = (got.double().cpu() - ref).abs().max().item()
         assert torch.isfinite(got.float()).all() and err <= tol * max(1.0, ref.abs().max().item()), (seed, name, err)
+
+
+@pytest.mark.parametrize("seed", range(6 * _MULT))
+def test_random_dense_many_items_per_cta(api, seed):
+    """More work items than SMs, of very different lengths: every persistent CTA walks several items, so the
+    cross-item pipeline (next item's loads under this item's epilogue, barrier phases carried across items) is
+    exercised the way the full-size configs do, but at a size the float64 oracle still checks element by element."""
+    rng = random.Random(5000 + seed)
+    dtype = rng.choice([torch.float16, torch.bfloat16])
+    D = rng.choice([64, 128, 128, 256])
+    B, H, Hk = 2, 12, rng.choice([2, 12])
+    Sq = rng.randint(1500, 2600)
+    Sk = Sq if rng.random() < 0.6 else rng.randint(1500, 2600)
+    causal = rng.random() < 0.7
+    window = (-1, -1) if rng.random() < 0.6 else (rng.randint(100, 900), rng.randint(0, 300) if not causal else 0)
+    torch.manual_seed(seed)
+    q = torch.randn(B, Sq, H, D, device="cuda", dtype=dtype)
+    k = torch.randn(B, Sk, Hk, D, device="cuda", dtype=dtype)
+    v = torch.randn(B, Sk, Hk, D, device="cuda", dtype=dtype)
+    out = api.flash_attn_func(q, k, v, causal=causal, window_size=window)
+    ref, _ = ao.flash_attn_func_ref(q, k, v, causal=causal, window_size=window)
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all() and err <= _tol(dtype), (seed, err)
