@@ -33,6 +33,17 @@ def _pad8(x: torch.Tensor, pad: int) -> torch.Tensor:
     return torch.nn.functional.pad(x, [0, pad]) if pad else x
 
 
+class _NoCtx:
+    """Stand-in for the autograd context when the forward runs outside autograd (no input requires grad)."""
+
+    @staticmethod
+    def mark_non_differentiable(*tensors):
+        return None
+
+
+_NO_CTX = _NoCtx()
+
+
 # ======================================================================================
 # DENSE ATTENTION (B, M, H, D)
 # ======================================================================================
@@ -118,9 +129,15 @@ def flash_attn_func(
         warnings.warn("Forward is always deterministic. Deterministic backward is not supported.", RuntimeWarning)
         deterministic = False
     try:
+        grad = torch.is_grad_enabled()
+        if not (grad and (q.requires_grad or k.requires_grad or v.requires_grad)):
+            # nothing to record: call the forward directly (autograd.Function.apply costs ~10 us per call, which is
+            # most of a small problem's latency); same code path, same results
+            return FlashAttnFunc.forward(_NO_CTX, q, k, v, dropout_p, softmax_scale, causal, window_size, softcap,
+                                         alibi_slopes, deterministic, return_attn_probs, False)
         return FlashAttnFunc.apply(
             q, k, v, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes,
-            deterministic, return_attn_probs, torch.is_grad_enabled(),
+            deterministic, return_attn_probs, grad,
         )
     except Exception as e:
         print(f"[B200 FA2 DENSE FAILED] {type(e).__name__}: {e}")
@@ -220,10 +237,15 @@ def flash_attn_varlen_func(
         warnings.warn("Forward is always deterministic. Deterministic backward is not supported.", RuntimeWarning)
         deterministic = False
     try:
+        grad = torch.is_grad_enabled()
+        if not (grad and (q.requires_grad or k.requires_grad or v.requires_grad)):
+            return FlashAttnVarlenFunc.forward(
+                _NO_CTX, q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale,
+                causal, window_size, softcap, alibi_slopes, deterministic, return_attn_probs, block_table, False)
         return FlashAttnVarlenFunc.apply(
             q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale,
             causal, window_size, softcap, alibi_slopes, deterministic, return_attn_probs, block_table,
-            torch.is_grad_enabled(),
+            grad,
         )
     except Exception as e:
         print(f"[B200 FA2 VARLEN FAILED] {type(e).__name__}: {e}")

@@ -135,9 +135,9 @@ def _dtype_code(t: torch.Tensor) -> int:
 def _call(fn_name: str, params: FaB200Params, device: torch.device) -> None:
     lib = load_library()
     params.struct_bytes = ctypes.sizeof(FaB200Params)
-    with torch.cuda.device(device):
-        stream = torch.cuda.current_stream(device).cuda_stream
-        rc = getattr(lib, fn_name)(ctypes.byref(params), ctypes.c_void_p(stream))
+    # the C layer selects `params.device` itself (and restores the caller's); no torch device guard is needed
+    stream = torch.cuda.current_stream(device).cuda_stream
+    rc = getattr(lib, fn_name)(ctypes.byref(params), ctypes.c_void_p(stream))
     if rc != 0:
         msg = lib.fa_b200_last_error().decode("utf-8", "replace")
         if rc == -2:
