@@ -62,7 +62,8 @@ def mha_backward_fixtures():
     executed verbatim in fp32 (upcast=True) on seed-421 fp16 inputs and an fp16 dO drawn after them
     (test.py:151-158)."""
     ref_mha_backward = load_ref_fn("ref_mha_backward")
-    for (B, H, M, N, D) in [(1, 1, 64, 64, 64), (1, 2, 128, 128, 128), (1, 2, 256, 256, 64)]:
+    for (B, H, M, N, D) in [(1, 1, 64, 64, 64), (1, 2, 128, 128, 128), (1, 2, 256, 256, 64), (1, 1, 32, 32, 32),
+                            (1, 1, 256, 256, 256)]:  # the last two: test.py:117, :120
         for causal in (False, True):
             torch.manual_seed(421)
             q = torch.randn(B, H, M, D, dtype=torch.float16)
@@ -79,7 +80,8 @@ def mha_backward_fixtures():
 
 def mha_fixtures():
     ref_mha_forward = load_ref_mha_forward()
-    for (B, H, M, N, D) in [(1, 1, 16, 16, 16), (1, 1, 64, 64, 64), (1, 2, 128, 128, 128), (1, 2, 256, 256, 64)]:
+    for (B, H, M, N, D) in [(1, 1, 16, 16, 16), (1, 1, 64, 64, 64), (1, 2, 128, 128, 128), (1, 2, 256, 256, 64),
+                            (1, 1, 32, 32, 32), (1, 1, 256, 256, 256)]:  # the last two: test.py:117, :120
         for causal in (False, True):
             torch.manual_seed(421)
             q = torch.randn(B, H, M, D, dtype=torch.float16)
