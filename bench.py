@@ -281,25 +281,58 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
     flops_all = sum(sharding.gather_checksums(flops_rank, dist, dev))  # whole-job work per step
     value = flops_all * args.steps / (max_ms * 1e-3) / 1e12
 
-    # ---- e2e: host pinned buffers -> H2D -> kernel -> D2H, pipelined over batch elements on two streams
+    # ---- e2e: host pinned buffers -> H2D -> kernel -> D2H through the public API, pipelined over batch elements.
+    # "3s" (default): a copy-in stream, a compute stream and a copy-out stream chained by events over NB buffer sets,
+    # so the H2D engine runs back to back; "2s": the first pipeline (two streams, each H2D -> kernel -> D2H).
+    # tools/e2e_probe.py measures both beside the raw PCIe copy rates.
     hq, hk, hv = (torch.randn(x.shape, dtype=torch.bfloat16).pin_memory() for x in (q, k, v))
     hout = torch.empty(q.shape, dtype=torch.bfloat16).pin_memory()
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    dq = [torch.empty_like(q[:1]) for _ in range(2)]
-    dk = [torch.empty_like(k[:1]) for _ in range(2)]
-    dv = [torch.empty_like(v[:1]) for _ in range(2)]
+    pipe = os.environ.get("FA_E2E_PIPE", "3s")
+    NB = 2 if pipe == "2s" else 3
+    dq = [torch.empty_like(q[:1]) for _ in range(NB)]
+    dk = [torch.empty_like(k[:1]) for _ in range(NB)]
+    dv = [torch.empty_like(v[:1]) for _ in range(NB)]
+    if pipe == "2s":
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
 
-    def e2e_step():
-        for b in range(B):
-            st = streams[b % 2]
-            with torch.cuda.stream(st):
-                dq[b % 2].copy_(hq[b:b + 1], non_blocking=True)
-                dk[b % 2].copy_(hk[b:b + 1], non_blocking=True)
-                dv[b % 2].copy_(hv[b:b + 1], non_blocking=True)
-                o = flash_attn_func(dq[b % 2], dk[b % 2], dv[b % 2], causal=causal, window_size=window)
-                hout[b:b + 1].copy_(o, non_blocking=True)
-        for st in streams:
-            st.synchronize()
+        def e2e_step():
+            for b in range(B):
+                st = streams[b % 2]
+                with torch.cuda.stream(st):
+                    dq[b % 2].copy_(hq[b:b + 1], non_blocking=True)
+                    dk[b % 2].copy_(hk[b:b + 1], non_blocking=True)
+                    dv[b % 2].copy_(hv[b:b + 1], non_blocking=True)
+                    o = flash_attn_func(dq[b % 2], dk[b % 2], dv[b % 2], causal=causal, window_size=window)
+                    hout[b:b + 1].copy_(o, non_blocking=True)
+            for st in streams:
+                st.synchronize()
+        e2e_note = "pipelined per batch element on 2 streams"
+    else:
+        s_in, s_c, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        loaded = [torch.cuda.Event() for _ in range(NB)]
+        consumed = [torch.cuda.Event() for _ in range(NB)]
+
+        def e2e_step():
+            for b in range(B):
+                i = b % NB
+                with torch.cuda.stream(s_in):
+                    if b >= NB:
+                        s_in.wait_event(consumed[i])  # the kernel that read this buffer set has finished
+                    dq[i].copy_(hq[b:b + 1], non_blocking=True)
+                    dk[i].copy_(hk[b:b + 1], non_blocking=True)
+                    dv[i].copy_(hv[b:b + 1], non_blocking=True)
+                    loaded[i].record(s_in)
+                with torch.cuda.stream(s_c):
+                    s_c.wait_event(loaded[i])
+                    o = flash_attn_func(dq[i], dk[i], dv[i], causal=causal, window_size=window)
+                    consumed[i].record(s_c)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(consumed[i])
+                    o.record_stream(s_out)
+                    hout[b:b + 1].copy_(o, non_blocking=True)
+            for st in (s_in, s_c, s_out):
+                st.synchronize()
+        e2e_note = f"pipelined per batch element: copy-in / compute / copy-out streams over {NB} buffer sets"
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
@@ -349,7 +382,7 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
                      "kernel": "fa_fwd_sm100_kernel<128,bf16>", "kernel_ms": kern_ms},
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "pinned host q,k,v -> H2D, kernel, out -> D2H, pipelined per batch element on 2 streams"},
+                "note": "pinned host q,k,v -> H2D, kernel, out -> D2H, " + e2e_note},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }

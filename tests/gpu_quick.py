@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Quick on-GPU diagnostic: a handful of shapes against the CPU oracle plus a coarse timing.
-Writes gpurun_out/quick.json. Not a test and not the bench -- a bring-up tool."""
+Writes gpurun_out/quick.json. Not collected by pytest and not the bench -- a bring-up checker; it lives under tests/ because only tests/,
+smoke() and the bench's cpu_baseline leg may import oracle/."""
 import json
 import os
 import sys
