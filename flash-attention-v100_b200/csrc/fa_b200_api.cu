@@ -81,18 +81,16 @@ int make_tmap(CUtensorMap* tm, int dtype, const void* ptr, int head_dim, int64_t
 }
 
 int check_device(int device) {
-    static int cached_major[64];
-    static bool cached[64];
+    static std::atomic<int> cached_major[64];  // 0 = not queried yet; threads may race to fill it with the same value
     if (device < 0 || device >= 64) return fail(FA_B200_EINVAL, "bad device ordinal %d", device);
-    if (!cached[device]) {
-        int major = 0;
+    int major = cached_major[device].load(std::memory_order_relaxed);
+    if (major == 0) {
         cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
         if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
-        cached_major[device] = major;
-        cached[device] = true;
+        cached_major[device].store(major, std::memory_order_relaxed);
     }
-    if (cached_major[device] != 10)
-        return fail(FA_B200_EARCH, "this library only runs on sm_100 (B200); device %d is sm_%dx", device, cached_major[device]);
+    if (major != 10)
+        return fail(FA_B200_EARCH, "this library only runs on sm_100 (B200); device %d is sm_%dx", device, major);
     return 0;
 }
 
@@ -239,13 +237,13 @@ int* next_sched_slot(int device) {
 }
 
 int sm_count(int device) {
-    static int cached[64];
-    if (cached[device & 63] == 0) {
-        int n = 0;
+    static std::atomic<int> cached[64];
+    int n = cached[device & 63].load(std::memory_order_relaxed);
+    if (n == 0) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
-        cached[device & 63] = n;
+        cached[device & 63].store(n, std::memory_order_relaxed);
     }
-    return cached[device & 63];
+    return n;
 }
 
 // Persistent 1-D grid; work items in sectioned longest-first order (see FwdKernelParams::section_bh).
