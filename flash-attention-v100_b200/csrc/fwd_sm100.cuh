@@ -130,6 +130,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; O is rescaled only whe
 #ifndef FA_SPLIT_P
 #define FA_SPLIT_P 1     // signal the MMA warp after 3/4 of P so P V starts before the last quarter
 #endif
+#ifndef FA_LD_OVERLAP
+#define FA_LD_OVERLAP 0  // softmax: split the S load so the row max of the first half overlaps the second half's load
+#endif
 #ifndef FA_EARLY_QK
 #define FA_EARLY_QK 1    // head_dim <= 64: issue the left half of the next S = Q K^T as soon as the softmax warps
 #endif                   // hold S in registers (see kEarlyQK)
@@ -658,7 +661,16 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 tc_fence_after();
                 FA_TRACE_EV(1);  // softmax: S observed
                 float v[BN];
-                tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
+                const bool need_mask = (j0 + BN > col_hi) || (j0 < col_lo);
+                const bool any_mask = __any_sync(0xffffffffu, need_mask);
+                // FA_LD_OVERLAP: the row max of columns [0,64) runs while columns [64,128) are still on their way
+                const bool split_ld = FA_LD_OVERLAP && !FEAT && !Cfg::kEarlyQK && !any_mask;
+                if (split_ld) {
+                    tmem_ld_2x32_wait(tS, reinterpret_cast<uint32_t*>(v));
+                    tmem_ld_2x32_nowait(tS + 64, reinterpret_cast<uint32_t*>(v + 64));
+                } else {
+                    tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
+                }
                 FA_TRACE_EV(2);  // softmax: S in registers
                 if (Cfg::kEarlyQK) {
                     tc_fence_before();
@@ -677,8 +689,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         v[c] = u * kLog2e;
                     }
                 }
-                const bool need_mask = (j0 + BN > col_hi) || (j0 < col_lo);
-                if (__any_sync(0xffffffffu, need_mask)) {
+                if (any_mask) {
                     const int base = j0 - col_lo;
 #pragma unroll
                     for (int c = 0; c < BN; ++c)
@@ -690,7 +701,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
 #pragma unroll
                 for (int a = 0; a < 4; ++a) mx[a] = fmaxf(v[2 * a], v[2 * a + 1]);
 #pragma unroll
-                for (int c = 8; c < BN; c += 8) {
+                for (int c = 8; c < BN / 2; c += 8) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) mx[a] = fmax3(mx[a], v[c + 2 * a], v[c + 2 * a + 1]);
+                }
+                if (split_ld) tmem_wait_ld_x64(reinterpret_cast<uint32_t*>(v + 64));
+#pragma unroll
+                for (int c = BN / 2; c < BN; c += 8) {
 #pragma unroll
                     for (int a = 0; a < 4; ++a) mx[a] = fmax3(mx[a], v[c + 2 * a], v[c + 2 * a + 1]);
                 }
