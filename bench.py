@@ -127,6 +127,53 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- reference arm
+def gpu_local_cpus(index: int):
+    """CPUs NVML reports as local to GPU `index` (its NUMA node), restricted to the CPUs this process may run on;
+    None when the box gives no topology (no NVML, a VM without NUMA information, an empty intersection)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+class numa_local:
+    """Runs the calling thread on the CPUs local to a GPU for the duration of the block, so that pinned host buffers
+    allocated inside it land on that GPU's NUMA node (first touch). With 8 ranks on a two-socket host, buffers on the
+    far socket put every H2D / D2H copy on the inter-socket link. Affinity is restored on exit; a no-op without
+    topology information."""
+
+    def __init__(self, index: int):
+        self.cpus = gpu_local_cpus(index)
+        self.prev = None
+        self.applied = False
+
+    def __enter__(self):
+        try:
+            self.prev = os.sched_getaffinity(0)
+            if self.cpus and self.cpus != self.prev:
+                os.sched_setaffinity(0, self.cpus)
+                self.applied = True
+        except Exception:  # noqa: BLE001
+            self.applied = False
+        return self
+
+    def __exit__(self, *a):
+        if self.applied:
+            try:
+                os.sched_setaffinity(0, self.prev)
+            except Exception:  # noqa: BLE001
+                pass
+        return False
+
+
 def cpu_reference_sample(w, threads: int):
     """One bounded sample of the workload on the host cores with the reference's own CPU attention
     (oracle/_ref, compiled from reference utils/sass/mma_swizzle/forward_kernel.cu:346-370); falls back to
@@ -285,8 +332,11 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
     # "3s" (default): a copy-in stream, a compute stream and a copy-out stream chained by events over NB buffer sets,
     # so the H2D engine runs back to back; "2s": the first pipeline (two streams, each H2D -> kernel -> D2H).
     # tools/e2e_probe.py measures both beside the raw PCIe copy rates.
-    hq, hk, hv = (torch.randn(x.shape, dtype=torch.bfloat16).pin_memory() for x in (q, k, v))
-    hout = torch.empty(q.shape, dtype=torch.bfloat16).pin_memory()
+    with numa_local(local_rank) as numa:
+        hq, hk, hv = (torch.randn(x.shape, dtype=torch.bfloat16).pin_memory() for x in (q, k, v))
+        hout = torch.empty(q.shape, dtype=torch.bfloat16).pin_memory()
+    print(f"[bench rank {rank}] pinned e2e buffers: gpu-local cpus={sorted(numa.cpus) if numa.cpus else None} "
+          f"bound={numa.applied}", file=sys.stderr, flush=True)
     pipe = os.environ.get("FA_E2E_PIPE", "3s")
     NB = 2 if pipe == "2s" else 3
     dq = [torch.empty_like(q[:1]) for _ in range(NB)]
@@ -382,7 +432,8 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
                      "kernel": "fa_fwd_sm100_kernel<128,bf16>", "kernel_ms": kern_ms},
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "pinned host q,k,v -> H2D, kernel, out -> D2H, " + e2e_note},
+                "note": "pinned host q,k,v -> H2D, kernel, out -> D2H, " + e2e_note,
+                "pinned_numa_local": bool(numa.applied)},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
