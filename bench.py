@@ -332,9 +332,13 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
     # "3s" (default): a copy-in stream, a compute stream and a copy-out stream chained by events over NB buffer sets,
     # so the H2D engine runs back to back; "2s": the first pipeline (two streams, each H2D -> kernel -> D2H).
     # tools/e2e_probe.py measures both beside the raw PCIe copy rates.
+    # the random data is made first, outside the bound block: torch's intra-op worker threads inherit the affinity of
+    # the thread that first needs them, and the CPU baseline below must keep every host core
+    host_src = [torch.randn(x.shape, dtype=torch.bfloat16) for x in (q, k, v)]
     with numa_local(local_rank) as numa:
-        hq, hk, hv = (torch.randn(x.shape, dtype=torch.bfloat16).pin_memory() for x in (q, k, v))
+        hq, hk, hv = (t.pin_memory() for t in host_src)
         hout = torch.empty(q.shape, dtype=torch.bfloat16).pin_memory()
+    del host_src
     print(f"[bench rank {rank}] pinned e2e buffers: gpu-local cpus={sorted(numa.cpus) if numa.cpus else None} "
           f"bound={numa.applied}", file=sys.stderr, flush=True)
     pipe = os.environ.get("FA_E2E_PIPE", "3s")
