@@ -65,12 +65,24 @@ int make_tmap(CUtensorMap* tm, int dtype, const void* ptr, int head_dim, int64_t
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA_B200_EARCH, "cuTensorMapEncodeTiled is not available from this driver");
     CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s must be 16-byte aligned", name);
-    CHECK_ARG(stride_h % 8 == 0 && stride_s % 8 == 0 && stride_b % 8 == 0,
-              "%s strides must be multiples of 8 elements (16 bytes)", name);
     cuuint64_t dims[4] = {(cuuint64_t)head_dim, (cuuint64_t)(heads > 0 ? heads : 1), (cuuint64_t)(rows > 0 ? rows : 1),
                           (cuuint64_t)(batch > 0 ? batch : 1)};
-    auto nz = [](int64_t s) { return (cuuint64_t)((s > 0 ? s : 8) * 2); };
-    cuuint64_t strides[3] = {nz(stride_h), nz(stride_s), nz(stride_b)};
+    // A dimension that is stepped over (extent > 1) needs a positive stride that is a multiple of 16 bytes: an
+    // expanded (stride-0) view cannot be described to TMA and must be materialised by the caller (the reference
+    // calls .contiguous()). A dimension of extent 1 is never stepped over; it gets a dummy 16-byte stride.
+    const int64_t in_strides[3] = {stride_h, stride_s, stride_b};
+    cuuint64_t strides[3];
+    for (int i = 0; i < 3; ++i) {
+        if (dims[i + 1] > 1) {
+            CHECK_ARG(in_strides[i] > 0, "%s has a non-positive stride (%lld) over a dimension of extent %llu: expanded / "
+                      "broadcast views are not supported, pass a materialised tensor", name, (long long)in_strides[i],
+                      (unsigned long long)dims[i + 1]);
+            CHECK_ARG(in_strides[i] % 8 == 0, "%s strides must be multiples of 8 elements (16 bytes)", name);
+            strides[i] = (cuuint64_t)in_strides[i] * 2;
+        } else {
+            strides[i] = 16;
+        }
+    }
     cuuint32_t box[4] = {64, (cuuint32_t)box_heads, (cuuint32_t)box_rows, 1};  // box_heads * box_rows == 128 tile rows
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(tm, dtype == FA_B200_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
@@ -120,7 +132,7 @@ int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) 
 int launch_fwd(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, bool feat, dim3 grid, cudaStream_t stream) {
     const bool bf16 = dtype == FA_B200_DTYPE_BF16;
     const int head_dim = tile_dim(real_head_dim);
-    if (kp.drop_thr != 0xffffffffu) {  // dropout on: one variant per (D, dtype), with the score-modifier path compiled in
+    if (kp.drop_thr != 0xffffffffu || kp.dmask != nullptr) {  // dropout on (a clamped threshold keeps everything but still writes dmask): one variant per (D, dtype), with the score-modifier path compiled in
         if (head_dim == 128 && bf16) return launch_fwd_t<128, true, true, false, true>(kp, grid, stream);
         if (head_dim == 128) return launch_fwd_t<128, false, true, false, true>(kp, grid, stream);
         if (head_dim == 64 && bf16) return launch_fwd_t<64, true, true, false, true>(kp, grid, stream);
@@ -218,23 +230,8 @@ int64_t decode_workspace_bytes(const fa_b200_params_t* p) {
     return ((rows * tile_dim(p->head_dim) * 4 + 255) & ~(int64_t)255) + ((rows * 4 + 255) & ~(int64_t)255);
 }
 
-// Scheduler state for the persistent kernel: one pair of ints (next work id, CTAs done) per launch.
-// A ring of 1024 pairs per device is allocated (8 KB, zeroed) the first time a device is used -- the only
-// allocation this library ever makes; each launch takes the next pair and the kernel re-zeroes it on exit,
-// so launches on concurrent streams never share a pair unless > 1024 of them are in flight at once.
-int* next_sched_slot(int device) {
-    static int* base[64];
-    static std::once_flag once[64];
-    static std::atomic<unsigned> counter[64];
-    std::call_once(once[device & 63], [&] {
-        int* ptr = nullptr;
-        if (cudaMalloc(&ptr, 1024 * 2 * sizeof(int)) == cudaSuccess && cudaMemset(ptr, 0, 1024 * 2 * sizeof(int)) == cudaSuccess)
-            base[device & 63] = ptr;
-    });
-    int* b = base[device & 63];
-    if (!b) return nullptr;
-    return b + 2 * (counter[device & 63].fetch_add(1, std::memory_order_relaxed) % 1024u);
-}
+// Debug counters of the forward kernel (tests only): see FwdKernelParams::dbg_counters.
+std::atomic<unsigned long long*> g_dbg_counters{nullptr};
 
 int sm_count(int device) {
     static std::atomic<int> cached[64];
@@ -246,7 +243,9 @@ int sm_count(int device) {
     return n;
 }
 
-// Persistent 1-D grid; work items in sectioned longest-first order (see FwdKernelParams::section_bh).
+// 1-D grid with one CTA per work item, in sectioned longest-first order (see FwdKernelParams::section_bh). Only
+// the CTAs that fit the GPU start; they stay persistent by cancelling the CTAs that have not started yet and taking
+// their work ids (cluster launch control, fwd_sm100.cuh), so no scheduler state lives in global memory.
 dim3 set_launch_order(fa::FwdKernelParams& kp, int device, int batch, int heads, int heads_k, int max_seqlen_q, int max_seqlen_k, int head_dim) {
     const int item_rows = tile_dim(head_dim) == 256 ? 128 : 256;  // FwdConfig<D>::kItemRows
     kp.num_m_blocks = (max_seqlen_q + item_rows - 1) / item_rows;
@@ -258,10 +257,10 @@ dim3 set_launch_order(fa::FwdKernelParams& kp, int device, int batch, int heads,
     if (sec < group) sec = group;
     if (sec > kp.num_bh) sec = kp.num_bh;
     kp.section_bh = (int)sec;
-    kp.sched = next_sched_slot(device);
+    (void)device;
+    kp.dbg_counters = g_dbg_counters.load(std::memory_order_relaxed);
     const int64_t total = (int64_t)kp.num_m_blocks * kp.num_bh;
-    const int sms = sm_count(device);
-    return dim3((unsigned)(total < sms ? total : sms), 1, 1);
+    return dim3((unsigned)total, 1, 1);
 }
 
 struct DeviceGuard {
@@ -322,6 +321,14 @@ void fill_common(fa::FwdKernelParams& kp, const fa_b200_params_t* p, bool causal
     kp.drop_thr = 0xffffffffu;  // keep everything
 }
 
+// Keep threshold of the dropout test `Philox word <= thr` (reference include/softmax.h:50-51 computes
+// (uint32_t)((1 - p) * 4294967295.0f) in float). The float product is 2^32 when 1 - p rounds to 1 (p < 2^-25),
+// which does not fit a uint32_t (undefined behaviour in the reference's expression): clamp it to 2^32 - 1.
+uint32_t drop_threshold(float p_dropout) {
+    const float t = (1.0f - p_dropout) * 4294967295.0f;
+    return t >= 4294967296.0f ? 0xffffffffu : static_cast<uint32_t>(t);
+}
+
 // Dropout state (reference include/softmax.h:50-51). `row_elems` = elements of one dmask row group.
 int fill_dropout(fa::FwdKernelParams& kp, const fa_b200_params_t* p, bool varlen) {
     CHECK_ARG(p->p_dropout >= 0.f && p->p_dropout < 1.f, "p_dropout must be in [0, 1)");
@@ -331,7 +338,7 @@ int fill_dropout(fa::FwdKernelParams& kp, const fa_b200_params_t* p, bool varlen
     }
     CHECK_ARG(p->softcap == 0.f, "Softcapping does not support dropout");
     kp.rp_dropout = 1.0f / (1.0f - p->p_dropout);
-    kp.drop_thr = static_cast<uint32_t>((1.0f - p->p_dropout) * 4294967295.0f);
+    kp.drop_thr = drop_threshold(p->p_dropout);
     kp.drop_seed = p->dropout_seed;
     kp.drop_offset = p->dropout_offset;
     kp.dmask = static_cast<uint16_t*>(p->dmask);
@@ -358,6 +365,13 @@ __attribute__((visibility("default"))) int fa_b200_debug_set_trace(void* dev_ptr
     return (int)cudaMemcpyToSymbol(fa::g_fa_trace, &p, sizeof(p));
 }
 #endif
+
+// Tests only: device pointer to two zero-initialised 64-bit counters ([0] softmax rows that crossed the lazy-rescale
+// threshold, [1] accumulator rescales executed), or NULL to switch counting off. Not part of the drop-in surface.
+__attribute__((visibility("default"))) int fa_b200_debug_set_counters(void* dev_ptr) {
+    g_dbg_counters.store(static_cast<unsigned long long*>(dev_ptr), std::memory_order_relaxed);
+    return 0;
+}
 
 FA_B200_API int fa_b200_abi_version(void) { return FA_B200_ABI_VERSION; }
 FA_B200_API const char* fa_b200_last_error(void) { return g_err; }
@@ -403,7 +417,6 @@ FA_B200_API int fa_b200_fwd(const fa_b200_params_t* p, void* stream_v) {
     if (int rc = fill_dropout(kp, p, false)) return rc;
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
     dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
-    if (!kp.sched) return fail(FA_B200_EINVAL, "could not allocate the 8 KB tile-scheduler buffer on device %d", p->device);
     return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
 }
 
@@ -456,7 +469,6 @@ FA_B200_API int fa_b200_varlen_fwd(const fa_b200_params_t* p, void* stream_v) {
     if (int rc = fill_dropout(kp, p, true)) return rc;
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
     dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
-    if (!kp.sched) return fail(FA_B200_EINVAL, "could not allocate the 8 KB tile-scheduler buffer on device %d", p->device);
     return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
 }
 
@@ -617,7 +629,6 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
     }
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
     dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
-    if (!kp.sched) return fail(FA_B200_EINVAL, "could not allocate the 8 KB tile-scheduler buffer on device %d", p->device);
     return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
 }
 
@@ -745,7 +756,7 @@ int bwd_common(const fa_b200_params_t* p, void* stream_v, bool varlen) {
     const bool dropout = p->p_dropout > 0.f;
     if (dropout) {
         kp.rp_dropout = 1.0f / (1.0f - p->p_dropout);
-        kp.drop_thr = static_cast<uint32_t>((1.0f - p->p_dropout) * 4294967295.0f);
+        kp.drop_thr = drop_threshold(p->p_dropout);
         kp.drop_seed = p->dropout_seed;
         kp.drop_offset = p->dropout_offset;
     }

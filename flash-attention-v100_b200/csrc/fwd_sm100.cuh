@@ -79,9 +79,12 @@ struct alignas(64) FwdKernelParams {
     int num_splits;      // CTAs along the KV length per (batch, kv head); > 1 => partial results
     float* o_partial;    // [split][batch][head][seqlen_q][D] fp32, normalised per split
     float* lse_partial;  // [split][batch][head][seqlen_q] fp32, -inf for an empty split
-    // persistent tile scheduler (non-decode): sched[0] = next work item to hand out, sched[1] = CTAs done;
-    // both are 0 before the launch and reset to 0 by the last CTA to finish.
-    int* sched;
+    // Tile scheduler (non-decode): the grid has one CTA per work item and the CTAs that get to run keep themselves
+    // persistent through cluster launch control -- each cancels a not-yet-started CTA of the grid and takes its
+    // work id (ptx_sm100.cuh: clc_try_cancel). There is no scheduler state in global memory.
+    // Debug counters (tests only; NULL in normal use): [0] += softmax rows whose running maximum moved past the
+    // lazy-rescale threshold, [1] += O-accumulator rescales executed by the correction warps (per warp).
+    unsigned long long* dbg_counters;
     // dropout (reference include/softmax.h:96-125, include/philox.h): keep iff Philox word <= drop_thr;
     // the 1/(1-p) factor is folded into the epilogue's 1/l. dmask: optional +-1.0 sign tensor.
     float rp_dropout;       // 1 / (1 - p); 1 when dropout is off
@@ -168,14 +171,15 @@ struct FwdConfig {
     static constexpr int kKvStages = (D == 256) ? 2 : (D == 128) ? 4 : 6;
     static constexpr int kSmemQ = kSplitD ? kTileBytes : 2 * kTileBytes;
     static constexpr int kSmemKV = kKvStages * kTileBytes;
-    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1 + 2;
+    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1 + 2 + 1;
     static constexpr int kOffBars = kSmemQ + kSmemKV;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
     static constexpr int kOffScale = (kOffTmemPtr + 16 + 15) & ~15;
     static constexpr int kOffRowSum = kOffScale + 2 * 128 * 4;      // [item parity][stage][128]
     static constexpr int kOffRowMax = kOffRowSum + 2 * 2 * 128 * 4;  // [item parity][stage][128]
-    static constexpr int kOffSched = kOffRowMax + 2 * 2 * 128 * 4;   // int[2] work ids
-    static constexpr int kSmemUsed = kOffSched + 16;
+    static constexpr int kOffSched = kOffRowMax + 2 * 2 * 128 * 4;   // int[2] work ids (+ 8 bytes of padding)
+    static constexpr int kOffClc = kOffSched + 16;                   // 16-byte cluster-launch-control response
+    static constexpr int kSmemUsed = kOffClc + 16;
     static constexpr int kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
     static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + kDO;
     static constexpr int kTmemPOff = 64;
@@ -364,7 +368,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     auto bar_sched_empty = [&](int b) { return bars + 8 * (kB0 + 17 + b); };  // everyone -> loader
     const uint32_t bar_vfix = bars + 8 * (kB0 + 19);  // sanitiser -> MMA: tail rows of the ragged V tile zeroed
     auto bar_s_loaded = [&](int s) { return bars + 8 * (kB0 + 20 + s); };  // softmax -> MMA: S_s is in registers
-    static_assert(kB0 + 22 <= Cfg::kNumBars, "barrier table too small");
+    const uint32_t bar_clc = bars + 8 * (kB0 + 22);  // launch unit -> loader: cancellation response landed
+    static_assert(kB0 + 23 <= Cfg::kNumBars, "barrier table too small");
+    const uint32_t sClc = sbase + Cfg::kOffClc;
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffTmemPtr);
     float* sScale = reinterpret_cast<float*>(sgen + Cfg::kOffScale);
     float* sRowSum = reinterpret_cast<float*>(sgen + Cfg::kOffRowSum);
@@ -387,6 +393,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         }
         mbar_init(bar_q_empty, 1);
         mbar_init(bar_vfix, 1);
+        mbar_init(bar_clc, 1);
         for (int i = 0; i < KV; ++i) {
             mbar_init(bar_kv_full(i), 1);
             mbar_init(bar_kv_empty(i), 1);
@@ -427,10 +434,30 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         int ring = 0;  // K of iteration it is ring entry (base + 2*it), V is (base + 2*it + 1)
         int ka = 0;    // items with work so far
         int id = DECODE ? 0 : (int)blockIdx.x;
-        auto fetch = [&]() -> int {  // next unclaimed work id (one atomic per CTA, broadcast to the warp)
-            int nid = 0;
-            if (lane == 0) nid = atomicAdd(p.sched, 1) + (int)gridDim.x;
-            return __shfl_sync(0xffffffffu, nid, 0);
+        // Work stealing through cluster launch control: ask for the blockIdx of a CTA that has not started
+        // yet; once a request fails (every CTA of the grid has started or was cancelled) no more are issued.
+        bool clc_more = !DECODE;
+        int clc_n = 0;  // requests issued so far (phase of bar_clc)
+        auto fetch_issue = [&]() {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar_clc, 16);
+                clc_try_cancel(sClc, bar_clc);
+            }
+        };
+        auto fetch_read = [&]() -> int {
+            mbar_wait(bar_clc, clc_n & 1);
+            ++clc_n;
+            uint32_t x = 0;
+            const bool ok = clc_query(sClc, x);
+            fence_proxy_async_smem();  // the response was read before the next request's async write
+            __syncwarp();
+            if (!ok) clc_more = false;
+            return ok ? (int)x : total_work;
+        };
+        auto fetch = [&]() -> int {
+            if (!clc_more) return total_work;
+            fetch_issue();
+            return fetch_read();
         };
         for (int k = 0;; ++k) {
             if constexpr (!DECODE) {
@@ -450,8 +477,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             }
             if (id >= total_work) break;
             const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
-            int next_id = total_work;
-            if constexpr (!DECODE) next_id = fetch();  // early: the atomic's latency hides behind the loads
+            const bool prefetching = clc_more;
+            if (prefetching) fetch_issue();  // early: the request's latency hides behind the loads
             if (w.n_tiles > 0) {
                 auto kv_coords = [&](int n, int& row, int& b) {
                     const int r = n * BN;
@@ -489,17 +516,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 }
                 ++ka;
             }
-            id = next_id;
-        }
-        if constexpr (!DECODE) {
-            // the last CTA to run out of work re-arms the scheduler for the next launch
-            if (lane == 0) {
-                const int done = atomicAdd(p.sched + 1, 1);
-                if (done == (int)gridDim.x - 1) {
-                    p.sched[0] = 0;
-                    p.sched[1] = 0;
-                }
-            }
+            id = prefetching ? fetch_read() : total_work;
         }
     } else if (warp == 12) {
         // ============================================================ MMA issuer
@@ -722,6 +739,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     if (d < -kRescaleThreshold) {
                         acc_scale = ex2_approx(d);
                         m_ref = m_new;
+                        if (p.dbg_counters) atomicAdd(p.dbg_counters, 1ull);
                     }
                 }
                 sScale[s * BM + row] = acc_scale;
@@ -860,6 +878,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     FA_TRACE_EV(200 + s);  // correction: stats observed
                     const float sc = sScale[s * BM + row];
                     if (j > 0 && __any_sync(0xffffffffu, sc != 1.0f)) {
+                        if (p.dbg_counters && lane == 0) atomicAdd(p.dbg_counters + 1, 1ull);
                         tc_fence_after();
 #pragma unroll
                         for (int c = 0; c < DO / 32; ++c) {

@@ -54,16 +54,61 @@ FA_DEVICE bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// -DFA_DEADLOCK_TRAP=<polls>: bring-up builds trap instead of spinning forever on a barrier that never flips.
+FA_DEVICE uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Every wait is bounded: a barrier that has not flipped after FA_WAIT_TIMEOUT_NS of wall-clock time (default
+// 10 s -- no dependency inside these kernels is ever legitimately that long) is a pipeline bug or a corrupted
+// launch, and the kernel traps (the host sees cudaErrorLaunchFailure at its next synchronisation) instead of
+// hanging the GPU. The clock is only read on the slow path, and only after a failed poll.
+// -DFA_WAIT_TIMEOUT_NS=0 removes the check; -DFA_DEADLOCK_TRAP=<polls> (bring-up) traps after a poll count.
+#ifndef FA_WAIT_TIMEOUT_NS
+#define FA_WAIT_TIMEOUT_NS 10000000000ull
+#endif
 FA_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
 #ifdef FA_DEADLOCK_TRAP
     for (uint32_t polls = 0; !mbar_try_wait(bar, parity); ++polls) {
         if (polls > (uint32_t)(FA_DEADLOCK_TRAP)) __trap();
     }
 #else
+    if (mbar_try_wait(bar, parity)) return;
+    // slow path: try_wait suspends the thread for a while before it gives up, so reading the clock per poll is cheap
+    const uint32_t t0 = (uint32_t)(globaltimer_ns() >> 20);  // ~ms units; one live register
     while (!mbar_try_wait(bar, parity)) {
+        if constexpr ((FA_WAIT_TIMEOUT_NS) != 0) {
+            if ((uint32_t)(globaltimer_ns() >> 20) - t0 > (uint32_t)((FA_WAIT_TIMEOUT_NS) >> 20)) __trap();
+        }
     }
 #endif
+}
+
+// ---------------------------------------------------------------- cluster launch control (sm_100)
+// Hardware work stealing for persistent kernels: a running CTA asks the launch unit to cancel a CTA of this
+// grid that has not started yet and, on success, receives that CTA's blockIdx and does its work. No global
+// counter, nothing to re-arm between launches, safe under CUDA-graph replay and concurrent streams.
+// The 16-byte response lands in shared memory through the async proxy and completes `bar` (expect 16 bytes).
+// After a FAILED request (nothing left to cancel) no further request may be issued by this CTA.
+FA_DEVICE void clc_try_cancel(uint32_t response_smem, uint32_t bar) {
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                 ::"r"(response_smem), "r"(bar) : "memory");
+}
+// Decodes a response: returns true and the cancelled CTA's blockIdx.x if the request succeeded.
+FA_DEVICE bool clc_query(uint32_t response_smem, uint32_t& ctaid_x) {
+    uint32_t ok, x;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b128 r;\n\t"
+        "ld.shared.b128 r, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, r;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "mov.u32 %1, 0;\n\t"
+        "@p clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %1, r;\n\t}\n"
+        : "=r"(ok), "=r"(x)
+        : "r"(response_smem)
+        : "memory");
+    ctaid_x = x;
+    return ok != 0;
 }
 
 // ---------------------------------------------------------------- proxies / fences

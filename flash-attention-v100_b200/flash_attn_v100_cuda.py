@@ -121,6 +121,17 @@ def launch_count() -> int:
     return int(load_library().fa_b200_launch_count())
 
 
+def debug_set_counters(buf: Optional[torch.Tensor]) -> None:
+    """Tests only: point the forward kernel's debug counters at `buf` (int64[2] on the GPU; [0] = softmax rows whose
+    running maximum crossed the lazy-rescale threshold, [1] = rescales of the O accumulator), or None to switch off."""
+    lib = load_library()
+    lib.fa_b200_debug_set_counters.restype = ctypes.c_int
+    lib.fa_b200_debug_set_counters.argtypes = [ctypes.c_void_p]
+    if buf is not None:
+        assert buf.is_cuda and buf.dtype == torch.int64 and buf.numel() >= 2 and buf.is_contiguous()
+    lib.fa_b200_debug_set_counters(ctypes.c_void_p(buf.data_ptr() if buf is not None else None))
+
+
 def _check(cond: bool, msg: str) -> None:
     # the reference raises c10::Error (a RuntimeError in Python) from TORCH_CHECK
     if not cond:
@@ -161,8 +172,11 @@ def _pad_last(x: Optional[torch.Tensor], d_to: int) -> Optional[torch.Tensor]:
 
 
 def _aligned(x: torch.Tensor) -> torch.Tensor:
-    """TMA needs a 16-byte aligned base and strides that are multiples of 8 elements."""
-    ok = x.stride(-1) == 1 and x.data_ptr() % 16 == 0 and all(s % 8 == 0 for s in x.stride()[:-1])
+    """TMA needs a 16-byte aligned base and positive strides that are multiples of 8 elements."""
+    # Expanded (stride-0) or negative-stride views cannot be described to TMA: copy them like the reference's
+    # .contiguous() does. A dimension of extent 1 may carry any stride (it is never stepped over).
+    ok = x.stride(-1) == 1 and x.data_ptr() % 16 == 0 and all(
+        n == 1 or (s > 0 and s % 8 == 0) for n, s in zip(x.shape[:-1], x.stride()[:-1]))
     return x if ok else x.contiguous()
 
 
@@ -290,7 +304,7 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k_, leftpad_k_
         _check(block_table_.stride(-1) == 1, "block_table must have contiguous last dimension")
         _check(k.dim() == 4 and v.dim() == 4, "paged k/v must be [num_blocks, page_block_size, H_K, D]")
         num_pages, page, Hk = k.shape[0], k.shape[1], k.shape[2]
-        _check(page % 256 == 0, "page_block_size must be a multiple of 256")
+        _check(page % 128 == 0, "page_block_size must be a multiple of 128")  # reference: 256; the C ABI takes any multiple of 128
         _check(block_table_.shape[0] == B, "block_table must have one row per sequence")
     else:
         Hk = k.shape[1]
@@ -309,18 +323,20 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k_, leftpad_k_
     if out_ is not None:
         _check(out_.dtype == q.dtype and out_.is_cuda and out_.stride(-1) == 1 and out_.shape == q.shape,
                "out must match q in dtype, device and shape with a contiguous last dimension")
-    if T == 0 or max_seqlen_q == 0:
+    if T == 0 or max_seqlen_q == 0 or max_seqlen_k == 0:
+        # reference ..._varlen.cu:537-545: zero_tensors zeroes out and fills lse with -inf before the early return;
+        # without it the reference returns uninitialised buffers -- here they are always defined (out = 0, lse = -inf)
         out = out_ if out_ is not None else torch.empty_like(q)
+        out.zero_()
+        lse.fill_(float("-inf"))
         return [out, lse, dmask, rng_state]
 
     qp, kp, vp = (_aligned(_pad_last(t, Dp)) for t in (q, k, v))
     direct = out_ is not None and Dp == D and _aligned(out_) is out_
     out = out_ if direct else torch.empty((T, H, Dp), dtype=q.dtype, device=q.device)
-    if zero_tensors or max_seqlen_k == 0:
+    if zero_tensors:  # reference ..._varlen.cu:537-541 (the kernel overwrites every row of every sequence afterwards)
         out.zero_()
-        lse.fill_(float("-inf") if not zero_tensors else 0.0)
-    if max_seqlen_k == 0:
-        return [out[..., :D] if not direct else out, lse, dmask, rng_state]
+        lse.fill_(float("-inf"))
 
     p = FaB200Params()
     keep = [qp, kp, vp, out, lse, cu_seqlens_q, cu_seqlens_k]
@@ -381,7 +397,7 @@ def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_,
         _check(cache_batch_idx_ is None, "Paged KV cache does not support cache_batch_idx")
         _check(leftpad_k_ is None, "Paged KV cache does not support cache_leftpad")
         num_pages, page, Hk = kcache.shape[0], kcache.shape[1], kcache.shape[2]
-        _check(page % 256 == 0, "page_block_size must be a multiple of 256")
+        _check(page % 128 == 0, "page_block_size must be a multiple of 128")  # reference: 256; the C ABI takes any multiple of 128
         _check(block_table_.shape[0] == B, "block_table must have one row per sequence")
         capacity = block_table_.shape[1] * page
         batch_c = 0

@@ -106,7 +106,9 @@ typedef struct fa_b200_params {
     /* paged KV (reference kernel/fused_mha_forward_varlen.cu:434-449, ..._kvcache.cu:484-500) */
     const int32_t* block_table; /* (batch, block_table_cols) page ids, or NULL */
     int32_t block_table_stride; /* elements between rows of block_table */
-    int32_t page_size;          /* rows per page; multiple of 256 as in the reference */
+    int32_t page_size;          /* rows per page; a multiple of 128 (one KV tile never straddles two pages). The
+                                   reference requires 256 (kernel/fused_mha_forward_kvcache.cu:506-509); every
+                                   page size it accepts is accepted here, and 128 / 384 / ... in addition */
     int32_t num_pages;
     int32_t reserved2;
 

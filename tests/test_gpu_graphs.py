@@ -85,3 +85,37 @@ def test_dense_forward_replays_from_a_cuda_graph(api):
         ref = api.flash_attn_func(q, k, v, causal=True)
         torch.cuda.synchronize()
         assert torch.equal(out_static, ref)
+
+
+def test_graph_replay_overlapping_many_eager_launches_on_another_stream(api):
+    """A captured forward keeps no per-launch scheduler state: replays may overlap any number of eager launches
+    on other streams (the round-1 scheduler took a counter from a 1024-slot ring, which a replay running beside
+    > 1024 eager launches could share; work is now handed out by cluster launch control, with no global state)."""
+    torch.manual_seed(13)
+    dt = torch.bfloat16
+    q = torch.randn(2, 2048, 16, 128, device="cuda", dtype=dt)  # 256 work items: more than the SM count
+    k = torch.randn(2, 2048, 4, 128, device="cuda", dtype=dt)
+    v = torch.randn(2, 2048, 4, 128, device="cuda", dtype=dt)
+    qs = torch.randn(1, 300, 2, 128, device="cuda", dtype=dt)
+    ref_big = api.flash_attn_func(q, k, v, causal=True).clone()
+    ref_small = api.flash_attn_func(qs, qs, qs, causal=True).clone()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out_static = api.flash_attn_func(q, k, v, causal=True)
+    side = torch.cuda.Stream()
+    for rep in range(3):
+        out_static.zero_()
+        torch.cuda.synchronize()
+        outs = []
+        for i in range(1200):
+            if i % 40 == 0:
+                g.replay()  # on the current stream, while the side stream keeps launching
+            with torch.cuda.stream(side):
+                o = api.flash_attn_func(qs, qs, qs, causal=True)
+                if i % 100 == 0:
+                    outs.append(o)
+        torch.cuda.synchronize()
+        assert torch.equal(out_static, ref_big), f"replay {rep}: captured forward corrupted by concurrent launches"
+        for o in outs:
+            assert torch.equal(o, ref_small)

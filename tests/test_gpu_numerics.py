@@ -1,0 +1,203 @@
+"""GPU parity away from benign logits: large scores, a late outlier key, expanded (stride-0) inputs.
+
+Every other GPU test feeds unit-variance inputs with scale D^-0.5, so a row's running maximum settles in the
+first KV tile and the lazy-rescale path of the forward (softmax warps: `d < -kRescaleThreshold`; correction
+warps: the O-accumulator rescale in TMEM) and the backward's `exp2(S*scale - lse)` away from O(1) arguments
+never run with a finite, non-trivial factor. These cases force them, in the plain (FEAT = false) kernel
+templates, and assert through the library's debug counters that the rescale really executed.
+
+Pass rules are the reference's own (test.py:273-277 forward, test.py:322-334 backward) against the float64
+oracle, plus an absolute bound on the forward (16-bit rounding of O(1) outputs).
+"""
+import pytest
+import torch
+
+from oracle import attention_oracle as ao
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(fa_lib):
+    import flash_attn_v100 as m
+
+    return m
+
+
+@pytest.fixture(scope="module")
+def op(fa_lib):
+    import flash_attn_v100_cuda as m
+
+    return m
+
+
+class _Counters:
+    """fa_b200_debug_set_counters: [0] rows whose maximum crossed the lazy-rescale threshold, [1] rescales of O."""
+
+    def __init__(self, op):
+        self.op = op
+        self.buf = torch.zeros(2, dtype=torch.int64, device="cuda")
+
+    def __enter__(self):
+        self.op.debug_set_counters(self.buf)
+        return self
+
+    def __exit__(self, *exc):
+        torch.cuda.synchronize()
+        self.op.debug_set_counters(None)
+
+    def read(self):
+        torch.cuda.synchronize()
+        return [int(x) for x in self.buf.tolist()]
+
+
+def _inputs(B, Sq, Sk, H, Hk, D, dtype, q_gain, outlier, seed=421):
+    torch.manual_seed(seed)
+    q = torch.randn(B, Sq, H, D, device="cuda", dtype=torch.float32) * q_gain
+    k = torch.randn(B, Sk, Hk, D, device="cuda", dtype=torch.float32)
+    v = torch.randn(B, Sk, Hk, D, device="cuda", dtype=torch.float32)
+    if outlier:
+        # One key in the FIRST KV tile (the kernel walks the tiles last to first, so it is met last) that every
+        # query scores ~ +40 nats above the rest: the running maximum jumps on the final tile of every row.
+        u = torch.zeros(D, device="cuda")
+        u[: D // 2] = 1.0
+        u = u / u.norm()
+        q = q + 6.0 * (D ** 0.25) * u
+        k[:, 5] = 6.0 * (D ** 0.25) * u * 1.1
+    return q.to(dtype), k.to(dtype), v.to(dtype)
+
+
+def _check_fwd(out, lse, q, k, v, causal):
+    D = q.shape[-1]
+    sc = D ** -0.5
+    ref, lse_ref = ao.flash_attn_func_ref(q, k, v, causal=causal)
+    wl, wr = ao.normalize_mask_args(q.shape[1], k.shape[1], causal, (-1, -1), False)
+    naive = ao.naive_lowp_attention(q, k, v, sc, wl, wr)
+    ok, err, err_naive = ao.fa_tolerance_ok(out, ref, naive)
+    assert ok, f"max err {err:.3e} > 2 * naive {err_naive:.3e} + 1e-5"
+    # outputs are convex combinations of N(0,1) rows of V: absolute error = 16-bit rounding of O and P
+    assert err <= (3e-2 if q.dtype == torch.bfloat16 else 4e-3), err
+    l = lse.double().cpu()
+    assert bool(((l - lse_ref).abs() <= 1e-3 * lse_ref.abs().clamp(min=1.0)).all()), (l - lse_ref).abs().max().item()
+
+
+CASES = [
+    # (q gain, outlier key)   logits are N(0, gain^2) nats
+    (6.0, False),
+    (12.0, False),
+    (1.0, True),
+    (6.0, True),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("q_gain,outlier", CASES)
+@pytest.mark.parametrize("D", [64, 128])
+def test_forward_large_logits_and_late_outlier(api, op, dtype, causal, q_gain, outlier, D):
+    B, S, H, Hk = 1, 1024, 4, 2
+    q, k, v = _inputs(B, S, S, H, Hk, D, dtype, q_gain, outlier)
+    with _Counters(op) as c:
+        o4, lse, _, _ = op.fwd(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), None, None, 0.0,
+                               D ** -0.5, causal, -1, -1, 0.0, False, None)
+        out = o4.permute(0, 2, 1, 3)
+        crossed, rescales = c.read()
+    _check_fwd(out, lse, q, k, v, causal)
+    # the point of the test: the lazy-rescale branch and the TMEM rescale of O ran with a finite factor
+    assert crossed > 0 and rescales > 0, (crossed, rescales)
+    if outlier and not causal:
+        # every row's maximum jumps by ~40 nats on the tile that holds the outlier (the last one visited)
+        assert crossed >= B * H * S, crossed
+
+
+@pytest.mark.parametrize("D", [128, 256])
+def test_forward_outlier_head_dim_256_and_long(api, op, D):
+    q, k, v = _inputs(1, 2048, 2048, 2, 1, D, torch.bfloat16, 3.0, True)
+    with _Counters(op) as c:
+        out = api.flash_attn_func(q, k, v, causal=True)
+        crossed, rescales = c.read()
+    ref, _ = ao.flash_attn_func_ref(q, k, v, causal=True)
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert err <= 3e-2, err
+    assert crossed > 0 and rescales > 0
+
+
+def _bwd_rule(got, ref, naive, name):
+    err = (got.double().cpu() - ref).abs().max().item()
+    err_naive = (naive.double().cpu() - ref).abs().max().item()
+    assert bool(torch.isfinite(got.float()).all()), name
+    assert err <= 3.0 * err_naive + 1e-4, f"{name}: err {err:.3e} > 3 * naive {err_naive:.3e} + 1e-4"
+    # relative to the largest reference entry (the rule used by the other backward tests for 16-bit grads)
+    scale = max(ref.abs().max().item(), 1e-6)
+    assert err <= (6e-2 if got.dtype == torch.bfloat16 else 1e-2) * scale, f"{name}: {err:.3e} vs max {scale:.3e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("q_gain,outlier", [(6.0, False), (12.0, False), (1.0, True)])
+def test_backward_large_logits_and_late_outlier(api, op, dtype, causal, q_gain, outlier):
+    B, S, H, Hk, D = 1, 512, 4, 4, 128  # the naive 16-bit yardstick (test.py:36-61) is MHA only
+    q, k, v = _inputs(B, S, S, H, Hk, D, dtype, q_gain, outlier)
+    torch.manual_seed(7)
+    dout = torch.randn(B, S, H, D, device="cuda", dtype=dtype)
+    q.requires_grad_(True), k.requires_grad_(True), v.requires_grad_(True)
+    out = api.flash_attn_func(q, k, v, causal=causal)
+    dq, dk, dv = torch.autograd.grad(out, (q, k, v), dout)
+    qd, kd, vd = q.detach(), k.detach(), v.detach()
+    rq, rk, rv = ao.flash_attn_bwd_ref(dout, qd, kd, vd, causal=causal)
+    nq, nk, nv = ao.naive_lowp_attention_bwd(qd, kd, vd, dout, D ** -0.5, causal)
+    _bwd_rule(dq, rq, nq, "dq")
+    _bwd_rule(dk, rk, nk, "dk")
+    _bwd_rule(dv, rv, nv, "dv")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# expanded (stride-0) inputs: TMA cannot describe them; the operator layer materialises them like the
+# reference's .contiguous() does, and the C ABI refuses them instead of reading the wrong memory.
+# ---------------------------------------------------------------------------------------------------------
+def test_expanded_kv_over_heads_and_batch(api):
+    torch.manual_seed(3)
+    B, S, H, D = 2, 300, 4, 128
+    q = torch.randn(B, S, H, D, device="cuda", dtype=torch.bfloat16)
+    k1 = torch.randn(1, S, 1, D, device="cuda", dtype=torch.bfloat16)
+    v1 = torch.randn(1, S, 1, D, device="cuda", dtype=torch.bfloat16)
+    k, v = k1.expand(B, S, H, D), v1.expand(B, S, H, D)  # stride 0 over batch and heads
+    assert k.stride(0) == 0 and k.stride(2) == 0
+    out = api.flash_attn_func(q, k, v, causal=True)
+    ref, _ = ao.flash_attn_func_ref(q, k.contiguous(), v.contiguous(), causal=True)
+    assert (out.double().cpu() - ref).abs().max().item() <= 2e-2
+
+
+def test_expanded_dout_from_mean(api):
+    torch.manual_seed(4)
+    B, S, H, D = 1, 256, 4, 64
+    q, k, v = (torch.randn(B, S, H, D, device="cuda", dtype=torch.float16, requires_grad=True) for _ in range(3))
+    out = api.flash_attn_func(q, k, v, causal=False)
+    out.float().mean(dim=1).sum().backward()  # the gradient of a mean arrives as an expanded tensor
+    dout = torch.full((B, S, H, D), 1.0 / S, device="cuda", dtype=torch.float16)
+    rq, rk, rv = ao.flash_attn_bwd_ref(dout, q.detach(), k.detach(), v.detach(), causal=False)
+    for got, ref, name in ((q.grad, rq, "dq"), (k.grad, rk, "dk"), (v.grad, rv, "dv")):
+        err = (got.double().cpu() - ref).abs().max().item()
+        assert err <= 1e-2 * max(ref.abs().max().item(), 1e-6) + 1e-6, (name, err)
+
+
+def test_c_abi_rejects_stride0_over_a_stepped_dimension(op):
+    import ctypes
+
+    q = torch.randn(1, 4, 128, 64, device="cuda", dtype=torch.float16)
+    k = torch.randn(1, 4, 128, 64, device="cuda", dtype=torch.float16)
+    out = torch.empty_like(q)
+    lse = torch.empty(1, 4, 128, device="cuda", dtype=torch.float32)
+    p = op.FaB200Params()
+    p.dtype, p.device = 0, 0
+    p.batch, p.seqlen_q, p.seqlen_k, p.num_heads, p.num_heads_k, p.head_dim = 1, 128, 128, 4, 4, 64
+    p.q, p.k, p.v, p.out, p.lse = q.data_ptr(), k.data_ptr(), k.data_ptr(), out.data_ptr(), lse.data_ptr()
+    for name in ("q", "k", "v", "o"):
+        setattr(p, f"{name}_stride_b", q.stride(0))
+        setattr(p, f"{name}_stride_h", q.stride(1))
+        setattr(p, f"{name}_stride_s", q.stride(2))
+    p.k_stride_h = 0  # "expanded over heads"
+    p.softmax_scale = 0.125
+    p.window_left = p.window_right = -1
+    with pytest.raises(RuntimeError, match="non-positive stride"):
+        op._call("fa_b200_fwd", p, q.device)
