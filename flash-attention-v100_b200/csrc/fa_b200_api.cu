@@ -10,11 +10,13 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
 #include "../../include/fa_b200.h"
 #include "fwd_sm100.cuh"
+#include "fwd2_sm100.cuh"
 #include "bwd_sm100.cuh"
 #include "kvcache_prep.cuh"
 
@@ -129,9 +131,64 @@ int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) 
     return 0;
 }
 
-int launch_fwd(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, bool feat, dim3 grid, cudaStream_t stream) {
+// Forward v2 (fwd2_sm100.cuh: one 128-row query tile per CTA, three score buffers, two alternating softmax groups,
+// optionally CTA pairs sharing their K/V stream through TMA multicast) can serve head dims 65..128 without score
+// modifiers or dropout. It is parity-clean (the whole GPU suite passes on it) but measured slower than the round-1
+// kernel on this hardware, so it is opt-in: FA_B200_FWD_KERNEL=2s (single CTAs) or =2p (CTA pairs) in the
+// environment, read once per process. Everything else runs the round-1 kernel.
+int fwd2_mode() {  // 0 = off, 1 = single CTAs, 2 = CTA pairs
+    static const int mode = [] {
+        const char* e = getenv("FA_B200_FWD_KERNEL");
+        if (e && e[0] == '2' && e[1] == 's') return 1;
+        if (e && e[0] == '2') return 2;
+        return 0;  // default: the round-1 kernel, which measures faster on every BASELINE shape (forward v2)
+    }();
+    return mode;
+}
+int fwd2_cluster(const fa_b200_params_t* p) {  // 0: not a v2 shape; else CTAs per cluster
+    if (fwd2_mode() == 0 || tile_dim(p->head_dim) != 128 || p->alibi_slopes != nullptr || p->softcap != 0.f ||
+        p->p_dropout != 0.f || p->dmask != nullptr)
+        return 0;
+    return fwd2_mode();
+}
+
+template <bool BF16, int CL>
+int launch_fwd2_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+    using Cfg = fa::Fwd2Config;
+    auto kern = fa::fa_fwd2_sm100_kernel<BF16, CL>;
+    static std::once_flag once[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t attr_err = cudaSuccess;
+    std::call_once(once[dev & 63], [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    });
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(smem)");
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(512, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, kp);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fa_fwd2_sm100_kernel launch");
+    return 0;
+}
+
+int launch_fwd(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, bool feat, dim3 grid, cudaStream_t stream, int v2 = 0) {
     const bool bf16 = dtype == FA_B200_DTYPE_BF16;
     const int head_dim = tile_dim(real_head_dim);
+    if (v2 == 2) return bf16 ? launch_fwd2_t<true, 2>(kp, grid, stream) : launch_fwd2_t<false, 2>(kp, grid, stream);
+    if (v2 == 1) return bf16 ? launch_fwd2_t<true, 1>(kp, grid, stream) : launch_fwd2_t<false, 1>(kp, grid, stream);
     if (kp.drop_thr != 0xffffffffu || kp.dmask != nullptr) {  // dropout on (a clamped threshold keeps everything but still writes dmask): one variant per (D, dtype), with the score-modifier path compiled in
         if (head_dim == 128 && bf16) return launch_fwd_t<128, true, true, false, true>(kp, grid, stream);
         if (head_dim == 128) return launch_fwd_t<128, false, true, false, true>(kp, grid, stream);
@@ -233,6 +290,75 @@ int64_t decode_workspace_bytes(const fa_b200_params_t* p) {
 // Debug counters of the forward kernel (tests only): see FwdKernelParams::dbg_counters.
 std::atomic<unsigned long long*> g_dbg_counters{nullptr};
 
+// Tile-scheduler counters (FwdKernelParams::sched): every launch with more work items than CTAs gets one 8-byte
+// counter of its own, zeroed by a cudaMemsetAsync on the launch stream right before the kernel, so a launch never
+// depends on what an earlier user of the slot left behind and the kernel has nothing to re-arm.
+//  * eager launches take slots round-robin from a ring of kEagerSlots: two launches could only share a live counter
+//    if kEagerSlots launches were enqueued while one kernel is still running;
+//  * launches recorded into a CUDA graph (cudaStreamIsCapturing) take slots from a separate pool that is never
+//    recycled: the slot pointer is baked into the graph for good, so it must never be handed to anybody else.
+//    Replays of one graph instance serialise on the device, and every replay re-runs its own memset node.
+// The pools (192 KB per device) are the only memory this library ever allocates; fa_b200_init(device) creates them
+// ahead of time (it must run outside stream capture; the first launch on a device calls it otherwise).
+constexpr unsigned kEagerSlots = 16384, kCaptureSlots = 8192;
+struct SchedPools {
+    int* eager = nullptr;
+    int* capture = nullptr;
+    std::atomic<unsigned> next_eager{0}, next_capture{0};
+};
+SchedPools g_pools[64];
+std::once_flag g_pools_once[64];
+cudaError_t g_pools_err[64];
+
+int init_pools(int device) {
+    std::call_once(g_pools_once[device & 63], [&] {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaError_t e = cudaSetDevice(device);
+        int* ptr = nullptr;
+        if (e == cudaSuccess) e = cudaMalloc(&ptr, (size_t)(kEagerSlots + kCaptureSlots) * 2 * sizeof(int));
+        if (e == cudaSuccess) {
+            g_pools[device & 63].eager = ptr;
+            g_pools[device & 63].capture = ptr + 2 * kEagerSlots;
+        }
+        if (prev >= 0 && prev != device) cudaSetDevice(prev);
+        g_pools_err[device & 63] = e;
+        if (e != cudaSuccess) cudaGetLastError();  // clear the sticky-free error state
+    });
+    if (g_pools_err[device & 63] != cudaSuccess)
+        return fail((int)g_pools_err[device & 63],
+                    "fa_b200_init(%d): could not allocate the tile-scheduler counters (%s); if the first call on this "
+                    "device happens under CUDA-graph capture, call fa_b200_init(device) once beforehand",
+                    device, cudaGetErrorString(g_pools_err[device & 63]));
+    return 0;
+}
+
+// Counter for one launch, zeroed on `stream`. *slot = nullptr when the launch needs none.
+int take_sched_slot(int device, cudaStream_t stream, int** slot) {
+    *slot = nullptr;
+    if (int rc = init_pools(device)) return rc;
+    SchedPools& pl = g_pools[device & 63];
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) {
+        cudaGetLastError();
+        st = cudaStreamCaptureStatusNone;
+    }
+    int* s;
+    if (st == cudaStreamCaptureStatusActive) {
+        const unsigned i = pl.next_capture.fetch_add(1, std::memory_order_relaxed);
+        if (i >= kCaptureSlots)
+            return fail(FA_B200_EUNSUPPORTED, "more than %u attention launches were recorded into CUDA graphs on device %d: "
+                        "the pool of per-launch scheduler counters for captured launches is exhausted", kCaptureSlots, device);
+        s = pl.capture + 2 * i;
+    } else {
+        s = pl.eager + 2 * (pl.next_eager.fetch_add(1, std::memory_order_relaxed) % kEagerSlots);
+    }
+    cudaError_t e = cudaMemsetAsync(s, 0, 2 * sizeof(int), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(scheduler counter)");
+    *slot = s;
+    return 0;
+}
+
 int sm_count(int device) {
     static std::atomic<int> cached[64];
     int n = cached[device & 63].load(std::memory_order_relaxed);
@@ -243,11 +369,10 @@ int sm_count(int device) {
     return n;
 }
 
-// 1-D grid with one CTA per work item, in sectioned longest-first order (see FwdKernelParams::section_bh). Only
-// the CTAs that fit the GPU start; they stay persistent by cancelling the CTAs that have not started yet and taking
-// their work ids (cluster launch control, fwd_sm100.cuh), so no scheduler state lives in global memory.
-dim3 set_launch_order(fa::FwdKernelParams& kp, int device, int batch, int heads, int heads_k, int max_seqlen_q, int max_seqlen_k, int head_dim) {
-    const int item_rows = tile_dim(head_dim) == 256 ? 128 : 256;  // FwdConfig<D>::kItemRows
+// Persistent 1-D grid; work items in sectioned longest-first order (see FwdKernelParams::section_bh).
+// `v2` = CTAs per work item of forward v2 (0: the round-1 kernel). A v2 pair takes a 256-row item, like the round-1 CTA.
+dim3 set_launch_order(fa::FwdKernelParams& kp, int device, int batch, int heads, int heads_k, int max_seqlen_q, int max_seqlen_k, int head_dim, int v2 = 0) {
+    const int item_rows = (v2 == 1 || tile_dim(head_dim) == 256) ? 128 : 256;  // FwdConfig<D>::kItemRows; v2 single CTA: one 128-row tile
     kp.num_m_blocks = (max_seqlen_q + item_rows - 1) / item_rows;
     kp.num_bh = batch * heads;
     // K+V bytes one kv head streams; keep a section's K/V within ~32 MB of the 126 MB L2
@@ -257,10 +382,26 @@ dim3 set_launch_order(fa::FwdKernelParams& kp, int device, int batch, int heads,
     if (sec < group) sec = group;
     if (sec > kp.num_bh) sec = kp.num_bh;
     kp.section_bh = (int)sec;
-    (void)device;
     kp.dbg_counters = g_dbg_counters.load(std::memory_order_relaxed);
+    kp.sched = nullptr;
     const int64_t total = (int64_t)kp.num_m_blocks * kp.num_bh;
+#if FA_SCHED_CLC
+    (void)device;
     return dim3((unsigned)total, 1, 1);
+#else
+    const int cl = v2 == 2 ? 2 : 1;
+    const int units = sm_count(device) / cl;  // CTAs, or CTA pairs, that fit the device at once
+    return dim3((unsigned)((total < units ? total : units) * cl), 1, 1);
+#endif
+}
+
+// A launch with more work items than CTAs needs a scheduler counter (not under FA_SCHED_CLC).
+int arm_scheduler(fa::FwdKernelParams& kp, dim3 grid, int device, cudaStream_t stream, int cl = 1) {
+#if !FA_SCHED_CLC
+    if ((int64_t)kp.num_m_blocks * kp.num_bh > (int64_t)grid.x / cl) return take_sched_slot(device, stream, &kp.sched);
+#endif
+    (void)grid; (void)device; (void)stream; (void)cl;
+    return 0;
 }
 
 struct DeviceGuard {
@@ -373,6 +514,12 @@ __attribute__((visibility("default"))) int fa_b200_debug_set_counters(void* dev_
     return 0;
 }
 
+FA_B200_API int fa_b200_init(int device) {
+    g_err[0] = 0;
+    if (int rc = check_device(device)) return rc;
+    return init_pools(device);
+}
+
 FA_B200_API int fa_b200_abi_version(void) { return FA_B200_ABI_VERSION; }
 FA_B200_API const char* fa_b200_last_error(void) { return g_err; }
 FA_B200_API int64_t fa_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -416,8 +563,10 @@ FA_B200_API int fa_b200_fwd(const fa_b200_params_t* p, void* stream_v) {
 
     if (int rc = fill_dropout(kp, p, false)) return rc;
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
-    dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
-    return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
+    const int v2 = fwd2_cluster(p);
+    dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim, v2);
+    if (int rc = arm_scheduler(kp, grid, p->device, stream, v2 == 2 ? 2 : 1)) return rc;
+    return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream, v2);
 }
 
 // ------------------------------------------------------------------------------------------ varlen
@@ -468,8 +617,10 @@ FA_B200_API int fa_b200_varlen_fwd(const fa_b200_params_t* p, void* stream_v) {
     }
     if (int rc = fill_dropout(kp, p, true)) return rc;
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
-    dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
-    return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
+    const int v2 = fwd2_cluster(p);
+    dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim, v2);
+    if (int rc = arm_scheduler(kp, grid, p->device, stream, v2 == 2 ? 2 : 1)) return rc;
+    return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream, v2);
 }
 
 // ------------------------------------------------------------------------------------------ kv-cache
@@ -628,8 +779,10 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
         return 0;
     }
     const bool feat = p->alibi_slopes != nullptr || p->softcap > 0.f;
-    dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim);
-    return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream);
+    const int v2 = fwd2_cluster(p);
+    dim3 grid = set_launch_order(kp, p->device, p->batch, p->num_heads, p->num_heads_k, p->seqlen_q, p->seqlen_k, p->head_dim, v2);
+    if (int rc = arm_scheduler(kp, grid, p->device, stream, v2 == 2 ? 2 : 1)) return rc;
+    return launch_fwd(kp, p->head_dim, p->dtype, feat, grid, stream, v2);
 }
 
 // ------------------------------------------------------------------------------------------ backward

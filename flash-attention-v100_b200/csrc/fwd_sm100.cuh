@@ -79,9 +79,14 @@ struct alignas(64) FwdKernelParams {
     int num_splits;      // CTAs along the KV length per (batch, kv head); > 1 => partial results
     float* o_partial;    // [split][batch][head][seqlen_q][D] fp32, normalised per split
     float* lse_partial;  // [split][batch][head][seqlen_q] fp32, -inf for an empty split
-    // Tile scheduler (non-decode): the grid has one CTA per work item and the CTAs that get to run keep themselves
-    // persistent through cluster launch control -- each cancels a not-yet-started CTA of the grid and takes its
-    // work id (ptx_sm100.cuh: clc_try_cancel). There is no scheduler state in global memory.
+    // Tile scheduler (non-decode). Default: persistent grid (one CTA per SM); CTA c starts with work id c and draws
+    // further ids from `sched[0]` (a counter private to this launch, zeroed on the launch stream right before the
+    // kernel; NULL when the grid already covers every item). Ids are numbered longest-first, and the counter hands
+    // them out in exactly that order. -DFA_SCHED_CLC=1 builds the stateless alternative: one CTA per work item, the
+    // running CTAs cancel not-yet-started ones through cluster launch control and take their ids -- measured 3 %
+    // (head_dim 128) to 9 % (head_dim 64) slower on causal shapes because the launch unit hands CTAs out only
+    // approximately in order (tools/ubench/clc_order.cu, profiles/experiments/README.md).
+    int* sched;
     // Debug counters (tests only; NULL in normal use): [0] += softmax rows whose running maximum moved past the
     // lazy-rescale threshold, [1] += O-accumulator rescales executed by the correction warps (per warp).
     unsigned long long* dbg_counters;
@@ -135,6 +140,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; O is rescaled only whe
 #endif
 #ifndef FA_LD_OVERLAP
 #define FA_LD_OVERLAP 0  // softmax: split the S load so the row max of the first half overlaps the second half's load
+#endif
+#ifndef FA_SCHED_CLC
+#define FA_SCHED_CLC 0   // 1: stateless tile scheduler through cluster launch control (see FwdKernelParams::sched)
 #endif
 #ifndef FA_EARLY_QK
 #define FA_EARLY_QK 1    // head_dim <= 64: issue the left half of the next S = Q K^T as soon as the softmax warps
@@ -376,8 +384,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     float* sRowSum = reinterpret_cast<float*>(sgen + Cfg::kOffRowSum);
     float* sRowMax = reinterpret_cast<float*>(sgen + Cfg::kOffRowMax);
     volatile int* sSched = reinterpret_cast<volatile int*>(sgen + Cfg::kOffSched);
+    volatile uint32_t* sWatch = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffSched + 8);  // progress, warps done
 
     if (warp == 13 && lane == 0) {
+        sWatch[0] = 0;
+        sWatch[1] = 0;
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_q_full(s), 1);
             mbar_init(bar_s_full(s), 1);
@@ -434,6 +445,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         int ring = 0;  // K of iteration it is ring entry (base + 2*it), V is (base + 2*it + 1)
         int ka = 0;    // items with work so far
         int id = DECODE ? 0 : (int)blockIdx.x;
+#if FA_SCHED_CLC
         // Work stealing through cluster launch control: ask for the blockIdx of a CTA that has not started
         // yet; once a request fails (every CTA of the grid has started or was cancelled) no more are issued.
         bool clc_more = !DECODE;
@@ -454,6 +466,20 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             if (!ok) clc_more = false;
             return ok ? (int)x : total_work;
         };
+#else
+        // next unclaimed work id from this launch's counter (one atomic per CTA, broadcast to the warp)
+        bool clc_more = !DECODE && p.sched != nullptr;
+        int pending_id = 0;
+        auto fetch_issue = [&]() {
+            int nid = 0;
+            if (lane == 0) nid = atomicAdd(p.sched, 1) + (int)gridDim.x;
+            pending_id = __shfl_sync(0xffffffffu, nid, 0);
+        };
+        auto fetch_read = [&]() -> int {
+            if (pending_id >= total_work) clc_more = false;
+            return pending_id < total_work ? pending_id : total_work;
+        };
+#endif
         auto fetch = [&]() -> int {
             if (!clc_more) return total_work;
             fetch_issue();
@@ -517,7 +543,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 ++ka;
             }
             id = prefetching ? fetch_read() : total_work;
+            if (lane == 0) watchdog_progress(sWatch);
         }
+        watchdog_role_done(sWatch);
     } else if (warp == 12) {
         // ============================================================ MMA issuer
         reg_dec<48>();
@@ -624,7 +652,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             steps[1] += w.it_hi[1] - w.it_lo[1];
             kfix += w.ragged_tail ? 1 : 0;
             ++ka;
+            if (lane == 0) watchdog_progress(sWatch);
         }
+        watchdog_role_done(sWatch);
     } else if (warp < 8) {
         // ============================================================ softmax (stage = warp / 4)
         reg_inc<192>();
@@ -831,6 +861,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             steps += my_n;
             ++items;
         }
+        watchdog_role_done(sWatch);
     } else if (warp < 12) {
         // ============================================================ correction + epilogue
         reg_dec<80>();
@@ -969,6 +1000,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 FA_TRACE_EV(220 + s);  // correction: epilogue of stage s stored
             }
         }
+        watchdog_role_done(sWatch);
     } else if (warp == 14) {
         // ============================================================ V sanitiser
         // P is exactly 0 for key columns past seqlen_k, but 0 * NaN = NaN: a KV cache is allowed to hold
@@ -998,8 +1030,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             }
             ring += 2 * w.n_tiles;
         }
+        watchdog_role_done(sWatch);
     } else {
-        reg_dec<48>();  // warp 15: spare
+        reg_dec<48>();  // warp 15: watchdog (ptx_sm100.cuh) -- traps the kernel if this CTA stops making progress
+        watchdog_run(sWatch, 15);
     }
 
     // ------------------------------------------------------------------ teardown

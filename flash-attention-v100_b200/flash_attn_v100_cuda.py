@@ -86,6 +86,7 @@ class FaB200Params(ctypes.Structure):
 EXPORTED_SYMBOLS = (
     "fa_b200_abi_version", "fa_b200_last_error", "fa_b200_workspace_bytes", "fa_b200_fwd",
     "fa_b200_varlen_fwd", "fa_b200_kvcache_fwd", "fa_b200_launch_count", "fa_b200_bwd", "fa_b200_varlen_bwd",
+    "fa_b200_init",
 )
 
 _lib = None
@@ -104,6 +105,9 @@ def load_library() -> ctypes.CDLL:
     lib.fa_b200_abi_version.restype = ctypes.c_int
     lib.fa_b200_last_error.restype = ctypes.c_char_p
     lib.fa_b200_launch_count.restype = ctypes.c_int64
+    if hasattr(lib, "fa_b200_init"):  # absent from round-1 builds loaded through FA_B200_LIB for A/B runs
+        lib.fa_b200_init.restype = ctypes.c_int
+        lib.fa_b200_init.argtypes = [ctypes.c_int]
     lib.fa_b200_workspace_bytes.restype = ctypes.c_int64
     lib.fa_b200_workspace_bytes.argtypes = [ctypes.POINTER(FaB200Params), ctypes.c_int]
     for name in ("fa_b200_fwd", "fa_b200_varlen_fwd", "fa_b200_kvcache_fwd", "fa_b200_bwd", "fa_b200_varlen_bwd"):

@@ -173,6 +173,12 @@ typedef struct fa_b200_params {
 
 FA_B200_API int fa_b200_abi_version(void);
 
+/* One-time per-device set-up: allocates the library's only device memory, 192 KB of per-launch tile-scheduler
+ * counters. Optional -- the first launch on a device does it implicitly -- except when that first launch would
+ * happen while a CUDA graph is being captured (cudaMalloc is not capturable): call it once before capturing.
+ * Replaces nothing in the reference (its kernels have no scheduler state). Returns 0 or an error code. */
+FA_B200_API int fa_b200_init(int device);
+
 /* Thread-local text of the last error returned on this thread ("" if none). */
 FA_B200_API const char* fa_b200_last_error(void);
 

@@ -129,7 +129,8 @@ def _bwd_rule(got, ref, naive, name):
     assert err <= 3.0 * err_naive + 1e-4, f"{name}: err {err:.3e} > 3 * naive {err_naive:.3e} + 1e-4"
     # relative to the largest reference entry (the rule used by the other backward tests for 16-bit grads)
     scale = max(ref.abs().max().item(), 1e-6)
-    assert err <= (6e-2 if got.dtype == torch.bfloat16 else 1e-2) * scale, f"{name}: {err:.3e} vs max {scale:.3e}"
+    # (+1e-4 as in the reference's rule: with one dominant key dS, and with it dQ and dK, is ~0 everywhere)
+    assert err <= (6e-2 if got.dtype == torch.bfloat16 else 1e-2) * scale + 1e-4, f"{name}: {err:.3e} vs max {scale:.3e}"
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -144,7 +145,7 @@ def test_backward_large_logits_and_late_outlier(api, op, dtype, causal, q_gain, 
     out = api.flash_attn_func(q, k, v, causal=causal)
     dq, dk, dv = torch.autograd.grad(out, (q, k, v), dout)
     qd, kd, vd = q.detach(), k.detach(), v.detach()
-    rq, rk, rv = ao.flash_attn_bwd_ref(dout, qd, kd, vd, causal=causal)
+    rq, rk, rv, _ = ao.flash_attn_bwd_ref(dout, qd, kd, vd, causal=causal)
     nq, nk, nv = ao.naive_lowp_attention_bwd(qd, kd, vd, dout, D ** -0.5, causal)
     _bwd_rule(dq, rq, nq, "dq")
     _bwd_rule(dk, rk, nk, "dk")
@@ -175,7 +176,7 @@ def test_expanded_dout_from_mean(api):
     out = api.flash_attn_func(q, k, v, causal=False)
     out.float().mean(dim=1).sum().backward()  # the gradient of a mean arrives as an expanded tensor
     dout = torch.full((B, S, H, D), 1.0 / S, device="cuda", dtype=torch.float16)
-    rq, rk, rv = ao.flash_attn_bwd_ref(dout, q.detach(), k.detach(), v.detach(), causal=False)
+    rq, rk, rv, _ = ao.flash_attn_bwd_ref(dout, q.detach(), k.detach(), v.detach(), causal=False)
     for got, ref, name in ((q.grad, rq, "dq"), (k.grad, rk, "dk"), (v.grad, rv, "dv")):
         err = (got.double().cpu() - ref).abs().max().item()
         assert err <= 1e-2 * max(ref.abs().max().item(), 1e-6) + 1e-6, (name, err)

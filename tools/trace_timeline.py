@@ -28,7 +28,9 @@ torch.cuda.synchronize()
 t = buf.cpu().view(16, 2048, 2)
 NAMES = {1: "S seen", 2: "S in regs", 3: "max+stats", 4: "P 3/4", 5: "P all", 100: "mma P0 seen", 101: "mma P1 seen",
          110: "mma P0 last", 111: "mma P1 last", 120: "mma QK0 issued", 121: "mma QK1 issued", 200: "corr stats0",
-         201: "corr stats1", 210: "corr O0 final", 211: "corr O1 final", 220: "corr epi0 done", 221: "corr epi1 done", 230: "corr got id", 231: "corr geom", 400: "ask work", 401: "work slot full", 240: "corr last chunk0", 241: "corr last chunk1", 242: "corr tma read done0", 243: "corr tma read done1", 130: "mma new item", 131: "mma Q0 landed", 132: "mma K0,Q1 landed", 300: "load wait qempty", 301: "load q free", 302: "load first issued"}
+         201: "corr stats1", 210: "corr O0 final", 211: "corr O1 final", 220: "corr epi0 done", 221: "corr epi1 done", 230: "corr got id", 231: "corr geom", 400: "ask work", 401: "work slot full", 240: "corr last chunk0", 241: "corr last chunk1", 242: "corr tma read done0", 243: "corr tma read done1", 130: "mma new item", 131: "mma Q0 landed", 132: "mma K0,Q1 landed", 300: "load wait qempty", 301: "load q free", 302: "load first issued",
+         102: "mma P2 seen", 122: "mma QK2 issued", 140: "mma K landed", 141: "mma V landed", 142: "mma PV issued",
+         310: "load slot free", 311: "load issued"}
 events = []
 for w in (0, 4, 8, 12, 13):
     for i in range(2048):
@@ -51,6 +53,13 @@ for w in (0, 4):
     for (e, c) in ev:
         seq.setdefault(e, []).append(c)
     n = min(len(seq.get(e, [])) for e in (1, 2, 3, 4, 5))
+    if n <= 12 and all(len(seq.get(e, [])) > 12 for e in (1, 2, 3, 5)):  # forward v2: no 3/4-P event
+        n2 = min(len(seq[e]) for e in (1, 2, 3, 5))
+        sl = slice(4, min(n2, 30) - 1)
+        d = lambda a, b: statistics.mean([y - x for x, y in zip(seq[a][sl], seq[b][sl])])
+        period = statistics.mean([y - x for x, y in zip(seq[1][4:min(n2, 30) - 1], seq[1][5:min(n2, 30)])])
+        print(f"warp {w}: S seen->regs {d(1, 2):.0f}  regs->max+handoff {d(2, 3):.0f}  max->P all {d(3, 5):.0f}  "
+              f"active {d(1, 5):.0f}  period {period:.0f}  wait-for-S {period - d(1, 5):.0f}")
     if n > 12:
         sl = slice(4, min(n, 30) - 1)
         d = lambda a, b: statistics.mean([y - x for x, y in zip(seq[a][sl], seq[b][sl])])
@@ -59,4 +68,5 @@ for w in (0, 4):
               f"active {d(1, 5):.0f}  period {period:.0f}  wait-for-S {period - d(1, 5):.0f}")
 mm = [(int(t[12, i, 0]), int(t[12, i, 1])) for i in range(2048) if int(t[12, i, 1]) != 0]
 print("mma events", len(mm))
-print("\n".join(out[200:260]))
+lo = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+print("\n".join(out[lo:lo + 90]))
