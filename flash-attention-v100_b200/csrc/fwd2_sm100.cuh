@@ -62,7 +62,8 @@ struct Fwd2Config {
     static constexpr int kBarVfix = kBarSchedEmpty + 2;
     static constexpr int kBarInboxFull = kBarVfix + 1;       // [2]        leader's loader -> peer's loader (work id posted)
     static constexpr int kBarInboxEmpty = kBarInboxFull + 2; // [2]        peer's loader -> leader's loader (work id read)
-    static constexpr int kNumBars = kBarInboxEmpty + 2;
+    static constexpr int kBarDone = kBarInboxEmpty + 2;      //            role warps -> watchdog
+    static constexpr int kNumBars = kBarDone + 1;
     static constexpr int kOffBars = kSmemQ + kSmemKV;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
     static constexpr int kOffScale = (kOffTmemPtr + 16 + 15) & ~15;  // [3 slots][128]   O rescale factor of a tile
@@ -149,6 +150,7 @@ fa_fwd2_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     const uint32_t bar_vfix = bar(Cfg::kBarVfix);
     auto bar_inbox_full = [&](int b) { return bar(Cfg::kBarInboxFull + b); };
     auto bar_inbox_empty = [&](int b) { return bar(Cfg::kBarInboxEmpty + b); };
+    const uint32_t bar_done = bar(Cfg::kBarDone);
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffTmemPtr);
     float* sScale = reinterpret_cast<float*>(sgen + Cfg::kOffScale);
     float* sMref = reinterpret_cast<float*>(sgen + Cfg::kOffMref);
@@ -186,6 +188,7 @@ fa_fwd2_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         for (int i = 0; i < 16; ++i) mbar_init(bar(Cfg::kBarFinal + i), 1);
         mbar_init(bar_pv_done, 1);
         mbar_init(bar_vfix, 1);
+        mbar_init(bar_done, 15);
         mbar_fence_init();
         tma_prefetch_desc(&p.tm_q);
         tma_prefetch_desc(&p.tm_k);
@@ -311,7 +314,7 @@ fa_fwd2_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             }
             id = next_id;
         }
-        watchdog_role_done(sWatch);
+        watchdog_role_done(bar_done);
     } else if (warp == 12) {
         // ============================================================ MMA issuer
         reg_dec<48>();
@@ -452,7 +455,7 @@ fa_fwd2_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             q_ready = q_ready_next;
             if (lane == 0) watchdog_progress(sWatch);
         }
-        watchdog_role_done(sWatch);
+        watchdog_role_done(bar_done);
     } else if (warp < 8) {
         // ============================================================ softmax groups (group = warp / 4 takes tiles of its parity)
         reg_inc<192>();
@@ -586,7 +589,7 @@ fa_fwd2_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             }
             g += no;
         }
-        watchdog_role_done(sWatch);
+        watchdog_role_done(bar_done);
     } else if (warp < 12) {
         // ============================================================ correction + epilogue
         reg_dec<80>();
@@ -702,7 +705,7 @@ fa_fwd2_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             FA_TRACE_EV(220);
             g += no;
         }
-        watchdog_role_done(sWatch);
+        watchdog_role_done(bar_done);
     } else if (warp == 14) {
         // ============================================================ V sanitiser (see fwd_sm100.cuh)
         reg_dec<48>();
@@ -729,10 +732,10 @@ fa_fwd2_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             }
             ring += 2 * n;
         }
-        watchdog_role_done(sWatch);
+        watchdog_role_done(bar_done);
     } else {
         reg_dec<48>();  // warp 15: watchdog (ptx_sm100.cuh)
-        watchdog_run(sWatch, 15, sWaitDbg, p.dbg_counters);
+        watchdog_run(sWatch, bar_done, sWaitDbg, p.dbg_counters);
     }
 #undef FA_WAIT
 #undef FA_WAIT_CL

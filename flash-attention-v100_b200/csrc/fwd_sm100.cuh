@@ -179,7 +179,7 @@ struct FwdConfig {
     static constexpr int kKvStages = (D == 256) ? 2 : (D == 128) ? 4 : 6;
     static constexpr int kSmemQ = kSplitD ? kTileBytes : 2 * kTileBytes;
     static constexpr int kSmemKV = kKvStages * kTileBytes;
-    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1 + 2 + 1;
+    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1 + 2 + 1 + 1;
     static constexpr int kOffBars = kSmemQ + kSmemKV;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
     static constexpr int kOffScale = (kOffTmemPtr + 16 + 15) & ~15;
@@ -377,7 +377,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     const uint32_t bar_vfix = bars + 8 * (kB0 + 19);  // sanitiser -> MMA: tail rows of the ragged V tile zeroed
     auto bar_s_loaded = [&](int s) { return bars + 8 * (kB0 + 20 + s); };  // softmax -> MMA: S_s is in registers
     const uint32_t bar_clc = bars + 8 * (kB0 + 22);  // launch unit -> loader: cancellation response landed
-    static_assert(kB0 + 23 <= Cfg::kNumBars, "barrier table too small");
+    const uint32_t bar_done = bars + 8 * (kB0 + 23);  // role warps -> watchdog: this warp has left its loop
+    static_assert(kB0 + 24 <= Cfg::kNumBars, "barrier table too small");
     const uint32_t sClc = sbase + Cfg::kOffClc;
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffTmemPtr);
     float* sScale = reinterpret_cast<float*>(sgen + Cfg::kOffScale);
@@ -405,6 +406,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         mbar_init(bar_q_empty, 1);
         mbar_init(bar_vfix, 1);
         mbar_init(bar_clc, 1);
+        mbar_init(bar_done, 15);
         for (int i = 0; i < KV; ++i) {
             mbar_init(bar_kv_full(i), 1);
             mbar_init(bar_kv_empty(i), 1);
@@ -545,7 +547,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             id = prefetching ? fetch_read() : total_work;
             if (lane == 0) watchdog_progress(sWatch);
         }
-        watchdog_role_done(sWatch);
+        watchdog_role_done(bar_done);
     } else if (warp == 12) {
         // ============================================================ MMA issuer
         reg_dec<48>();
@@ -654,7 +656,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             ++ka;
             if (lane == 0) watchdog_progress(sWatch);
         }
-        watchdog_role_done(sWatch);
+        watchdog_role_done(bar_done);
     } else if (warp < 8) {
         // ============================================================ softmax (stage = warp / 4)
         reg_inc<192>();
@@ -861,7 +863,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             steps += my_n;
             ++items;
         }
-        watchdog_role_done(sWatch);
+        watchdog_role_done(bar_done);
     } else if (warp < 12) {
         // ============================================================ correction + epilogue
         reg_dec<80>();
@@ -1000,7 +1002,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 FA_TRACE_EV(220 + s);  // correction: epilogue of stage s stored
             }
         }
-        watchdog_role_done(sWatch);
+        watchdog_role_done(bar_done);
     } else if (warp == 14) {
         // ============================================================ V sanitiser
         // P is exactly 0 for key columns past seqlen_k, but 0 * NaN = NaN: a KV cache is allowed to hold
@@ -1030,10 +1032,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             }
             ring += 2 * w.n_tiles;
         }
-        watchdog_role_done(sWatch);
+        watchdog_role_done(bar_done);
     } else {
         reg_dec<48>();  // warp 15: watchdog (ptx_sm100.cuh) -- traps the kernel if this CTA stops making progress
-        watchdog_run(sWatch, 15);
+        watchdog_run(sWatch, bar_done);
     }
 
     // ------------------------------------------------------------------ teardown

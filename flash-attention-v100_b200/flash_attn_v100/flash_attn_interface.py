@@ -44,6 +44,43 @@ class _NoCtx:
 _NO_CTX = _NoCtx()
 
 
+# --------------------------------------------------------------------------------------
+# torch.compile: while dynamo traces, the API goes through the functional dispatcher operators
+# torch.ops.fa_b200.* (fake kernels + registered autograd formulas, flash_attn_v100_cuda.register_functional_ops),
+# so `torch.compile(fullgraph=True)` sees one opaque, differentiable node per attention call instead of ctypes.
+# Eager calls keep the direct path below (no dispatcher round trip; it matters for small problems).
+# --------------------------------------------------------------------------------------
+def _compiling() -> bool:
+    return torch.compiler.is_compiling()
+
+
+def _dense_traced(q, k, v, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, return_attn_probs):
+    head_size_og = q.shape[-1]
+    pad = (8 - head_size_og % 8) % 8
+    q_, k_, v_ = (_pad8(maybe_contiguous(t), pad).permute(0, 2, 1, 3) for t in (q, k, v))
+    if softmax_scale is None:
+        softmax_scale = head_size_og ** -0.5
+    out_, lse, dmask, _ = torch.ops.fa_b200.fwd(q_, k_, v_, alibi_slopes, dropout_p, softmax_scale, causal,
+                                                window_size[0], window_size[1], softcap, return_attn_probs)
+    out = out_[..., :head_size_og].permute(0, 2, 1, 3).contiguous()
+    return (out, lse, dmask) if return_attn_probs else out
+
+
+def _varlen_traced(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale, causal,
+                   window_size, softcap, alibi_slopes, return_attn_probs, block_table):
+    head_size_og = q.size(2)
+    pad = (8 - head_size_og % 8) % 8
+    q_, k_, v_ = (_pad8(maybe_contiguous(t), pad) for t in (q, k, v))
+    if softmax_scale is None:
+        softmax_scale = head_size_og ** -0.5
+    out_, lse, dmask, _ = torch.ops.fa_b200.varlen_fwd(
+        q_, k_, v_, cu_seqlens_q.to(torch.int32).contiguous(), cu_seqlens_k.to(torch.int32).contiguous(), block_table,
+        alibi_slopes, max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale, causal, window_size[0], window_size[1],
+        softcap, return_attn_probs and dropout_p > 0.0)
+    out = out_[..., :head_size_og].contiguous()
+    return (out, lse, dmask) if return_attn_probs else out
+
+
 # ======================================================================================
 # DENSE ATTENTION (B, M, H, D)
 # ======================================================================================
@@ -128,6 +165,8 @@ def flash_attn_func(
         # the reference warns and clears the flag (:129-131); this build's backward is deterministic anyway
         warnings.warn("Forward is always deterministic. Deterministic backward is not supported.", RuntimeWarning)
         deterministic = False
+    if _compiling():
+        return _dense_traced(q, k, v, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, return_attn_probs)
     try:
         grad = torch.is_grad_enabled()
         if not (grad and (q.requires_grad or k.requires_grad or v.requires_grad)):
@@ -236,6 +275,9 @@ def flash_attn_varlen_func(
     if deterministic:
         warnings.warn("Forward is always deterministic. Deterministic backward is not supported.", RuntimeWarning)
         deterministic = False
+    if _compiling():
+        return _varlen_traced(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, dropout_p, softmax_scale,
+                              causal, window_size, softcap, alibi_slopes, return_attn_probs, block_table)
     try:
         grad = torch.is_grad_enabled()
         if not (grad and (q.requires_grad or k.requires_grad or v.requires_grad)):
@@ -292,6 +334,12 @@ def flash_attn_with_kvcache(
     def _c(t):
         return t.contiguous() if t is not None else None
 
+    if _compiling():
+        out, softmax_lse = torch.ops.fa_b200.fwd_kvcache(
+            q, k_cache, v_cache, k, v, _c(cache_seqlens), rotary_cos, rotary_sin, _c(cache_batch_idx),
+            _c(cache_leftpad), _c(block_table), alibi_slopes, softmax_scale, causal, window_size[0], window_size[1],
+            softcap, rotary_interleaved, num_splits)
+        return (out, softmax_lse) if return_softmax_lse else out
     out, softmax_lse = flash_attn_v100_cuda.fwd_kvcache(
         q, k_cache, v_cache, k, v,
         _c(cache_seqlens), rotary_cos, rotary_sin,

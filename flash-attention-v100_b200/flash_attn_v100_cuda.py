@@ -37,7 +37,19 @@ from typing import List, Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.environ.get("FA_B200_LIB", os.path.join(_HERE, "lib", "libfa_b200.so"))
+def _find_library() -> str:
+    """FA_B200_LIB, else the in-tree build (lib/ next to this module), else the installed layout (the library
+    travels inside the flash_attn_v100 package: setup.py)."""
+    env = os.environ.get("FA_B200_LIB")
+    if env:
+        return env
+    for cand in (os.path.join(_HERE, "lib", "libfa_b200.so"), os.path.join(_HERE, "flash_attn_v100", "lib", "libfa_b200.so")):
+        if os.path.exists(cand):
+            return cand
+    return os.path.join(_HERE, "lib", "libfa_b200.so")
+
+
+_LIB_PATH = _find_library()
 
 FA_B200_DTYPE_FP16 = 0
 FA_B200_DTYPE_BF16 = 1
@@ -691,3 +703,177 @@ def register_torch_ops() -> bool:
 
 
 register_torch_ops()
+
+
+# ======================================================================================
+# torch.compile support. The reference registers its five operators with schemas that mark `q` as mutated
+# (`Tensor(a!) q`, kernel/fused_mha_api.cpp:308-358) and gives them neither a meta kernel nor an autograd formula, so
+# they cannot be traced or differentiated by the dispatcher; `torch.ops.flash_attn_v100.*` above mirrors that surface
+# (plus fake kernels, so at least shape propagation works). For `torch.compile(fullgraph=True)` the Python API routes
+# through FUNCTIONAL twins in the `fa_b200` namespace: same kernels, no Generator / optional-output arguments, fake
+# (meta) implementations, and autograd formulas registered with torch.library.register_autograd.
+# ======================================================================================
+def _like_strided(x: torch.Tensor, last: Optional[int] = None) -> torch.Tensor:
+    return torch.empty_like(x) if last is None or last == x.shape[-1] else x.new_empty((*x.shape[:-1], last))
+
+
+def _fake_fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, window_left, window_right, softcap,
+              return_softmax, gen_=None):
+    B, H, M, _ = q.shape
+    N = k.shape[2]
+    out = out_ if out_ is not None else torch.empty_like(q)
+    lse = q.new_empty((B, H, M), dtype=torch.float32)
+    dmask = q.new_empty((B, H, M, N)) if (return_softmax and p_dropout > 0.0) else q.new_empty((0,))
+    return [out, lse, dmask, q.new_empty((2,), dtype=torch.int64)]
+
+
+def _fake_bwd(dout, q, k, v, out, softmax_lse, dq_, dk_, dv_, alibi_slopes_, p_dropout, softmax_scale, is_causal,
+              window_left, window_right, softcap, deterministic, gen_=None, rng_state_=None):
+    B, H, M, _ = q.shape
+    return [dq_ if dq_ is not None else torch.empty_like(q), dk_ if dk_ is not None else torch.empty_like(k),
+            dv_ if dv_ is not None else torch.empty_like(v), q.new_empty((B, H, M), dtype=torch.float32)]
+
+
+def _fake_varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k_, leftpad_k_, block_table_, alibi_slopes_,
+                     max_seqlen_q, max_seqlen_k, p_dropout, softmax_scale, zero_tensors, is_causal, window_left,
+                     window_right, softcap, return_softmax, gen_=None, num_splits=0):
+    T, H, _ = q.shape
+    out = out_ if out_ is not None else torch.empty_like(q)
+    lse = q.new_empty((H, T), dtype=torch.float32)
+    dmask = q.new_empty((T, H, max_seqlen_k)) if (return_softmax and p_dropout > 0.0) else q.new_empty((0,))
+    return [out, lse, dmask, q.new_empty((2,), dtype=torch.int64)]
+
+
+def _fake_varlen_bwd(dout, q, k, v, out, softmax_lse, dq_, dk_, dv_, cu_seqlens_q, cu_seqlens_k, alibi_slopes_,
+                     max_seqlen_q, max_seqlen_k, p_dropout, softmax_scale, zero_tensors, is_causal, window_left,
+                     window_right, softcap, deterministic, gen_=None, rng_state_=None):
+    T, H, _ = q.shape
+    return [dq_ if dq_ is not None else torch.empty_like(q), dk_ if dk_ is not None else torch.empty_like(k),
+            dv_ if dv_ is not None else torch.empty_like(v), q.new_empty((H, T), dtype=torch.float32)]
+
+
+def _fake_fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_, cache_batch_idx_, leftpad_k_,
+                      block_table_, alibi_slopes_, out_, softmax_scale, is_causal, window_left, window_right, softcap,
+                      is_rotary_interleaved, num_splits):
+    B, Sq, H, _ = q.shape
+    out = out_ if out_ is not None else q.new_empty(q.shape)
+    return [out, q.new_empty((B, H, Sq), dtype=torch.float32)]
+
+
+_FUNCTIONAL_SCHEMAS = {
+    "fwd": "(Tensor q, Tensor k, Tensor v, Tensor? alibi_slopes, float p_dropout, float softmax_scale, bool is_causal, "
+           "int window_left, int window_right, float softcap, bool return_softmax) -> (Tensor, Tensor, Tensor, Tensor)",
+    "bwd": "(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor softmax_lse, Tensor? alibi_slopes, "
+           "float p_dropout, float softmax_scale, bool is_causal, int window_left, int window_right, float softcap, "
+           "Tensor? rng_state) -> (Tensor, Tensor, Tensor, Tensor)",
+    "varlen_fwd": "(Tensor q, Tensor k, Tensor v, Tensor cu_seqlens_q, Tensor cu_seqlens_k, Tensor? block_table, "
+                  "Tensor? alibi_slopes, int max_seqlen_q, int max_seqlen_k, float p_dropout, float softmax_scale, "
+                  "bool is_causal, int window_left, int window_right, float softcap, bool return_softmax) "
+                  "-> (Tensor, Tensor, Tensor, Tensor)",
+    "varlen_bwd": "(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor softmax_lse, Tensor cu_seqlens_q, "
+                  "Tensor cu_seqlens_k, Tensor? alibi_slopes, int max_seqlen_q, int max_seqlen_k, float p_dropout, "
+                  "float softmax_scale, bool is_causal, int window_left, int window_right, float softcap, "
+                  "Tensor? rng_state) -> (Tensor, Tensor, Tensor, Tensor)",
+    "fwd_kvcache": "(Tensor q, Tensor(a!) kcache, Tensor(b!) vcache, Tensor? k, Tensor? v, Tensor? seqlens_k, "
+                   "Tensor? rotary_cos, Tensor? rotary_sin, Tensor? cache_batch_idx, Tensor? leftpad_k, "
+                   "Tensor? block_table, Tensor? alibi_slopes, float softmax_scale, bool is_causal, int window_left, "
+                   "int window_right, float softcap, bool is_rotary_interleaved, int num_splits) -> (Tensor, Tensor)",
+}
+_functional_ops_registered = False
+
+
+def register_functional_ops() -> bool:
+    """torch.ops.fa_b200.{fwd,bwd,varlen_fwd,varlen_bwd,fwd_kvcache}: traceable, differentiable twins of the operators
+    (see the comment above). Also gives torch.ops.flash_attn_v100.* fake kernels. Idempotent."""
+    global _functional_ops_registered
+    if _functional_ops_registered:
+        return True
+    L = torch.library
+
+    def f_fwd(q, k, v, alibi_slopes, p_dropout, softmax_scale, is_causal, window_left, window_right, softcap, return_softmax):
+        return tuple(fwd(q, k, v, None, alibi_slopes, p_dropout, softmax_scale, is_causal, window_left, window_right,
+                         softcap, return_softmax, None))
+
+    def f_bwd(dout, q, k, v, out, softmax_lse, alibi_slopes, p_dropout, softmax_scale, is_causal, window_left,
+              window_right, softcap, rng_state):
+        return tuple(bwd(dout, q, k, v, out, softmax_lse, None, None, None, alibi_slopes, p_dropout, softmax_scale,
+                         is_causal, window_left, window_right, softcap, False, None, rng_state))
+
+    def f_varlen_fwd(q, k, v, cu_seqlens_q, cu_seqlens_k, block_table, alibi_slopes, max_seqlen_q, max_seqlen_k,
+                     p_dropout, softmax_scale, is_causal, window_left, window_right, softcap, return_softmax):
+        return tuple(varlen_fwd(q, k, v, None, cu_seqlens_q, cu_seqlens_k, None, None, block_table, alibi_slopes,
+                                max_seqlen_q, max_seqlen_k, p_dropout, softmax_scale, False, is_causal, window_left,
+                                window_right, softcap, return_softmax, None, 0))
+
+    def f_varlen_bwd(dout, q, k, v, out, softmax_lse, cu_seqlens_q, cu_seqlens_k, alibi_slopes, max_seqlen_q,
+                     max_seqlen_k, p_dropout, softmax_scale, is_causal, window_left, window_right, softcap, rng_state):
+        return tuple(varlen_bwd(dout, q, k, v, out, softmax_lse, None, None, None, cu_seqlens_q, cu_seqlens_k,
+                                alibi_slopes, max_seqlen_q, max_seqlen_k, p_dropout, softmax_scale, False, is_causal,
+                                window_left, window_right, softcap, False, None, rng_state))
+
+    def f_kvcache(q, kcache, vcache, k, v, seqlens_k, rotary_cos, rotary_sin, cache_batch_idx, leftpad_k, block_table,
+                  alibi_slopes, softmax_scale, is_causal, window_left, window_right, softcap, is_rotary_interleaved,
+                  num_splits):
+        return tuple(fwd_kvcache(q, kcache, vcache, k, v, seqlens_k, rotary_cos, rotary_sin, cache_batch_idx, leftpad_k,
+                                 block_table, alibi_slopes, None, softmax_scale, is_causal, window_left, window_right,
+                                 softcap, is_rotary_interleaved, num_splits))
+
+    impls = {"fwd": f_fwd, "bwd": f_bwd, "varlen_fwd": f_varlen_fwd, "varlen_bwd": f_varlen_bwd, "fwd_kvcache": f_kvcache}
+    fakes = {
+        "fwd": lambda q, k, v, a, p, s, c, wl, wr, sc, rs: tuple(_fake_fwd(q, k, v, None, a, p, s, c, wl, wr, sc, rs)),
+        "bwd": lambda do, q, k, v, o, lse, a, p, s, c, wl, wr, sc, rng: tuple(
+            _fake_bwd(do, q, k, v, o, lse, None, None, None, a, p, s, c, wl, wr, sc, False)),
+        "varlen_fwd": lambda q, k, v, cq, ck, bt, a, mq, mk, p, s, c, wl, wr, sc, rs: tuple(
+            _fake_varlen_fwd(q, k, v, None, cq, ck, None, None, bt, a, mq, mk, p, s, False, c, wl, wr, sc, rs)),
+        "varlen_bwd": lambda do, q, k, v, o, lse, cq, ck, a, mq, mk, p, s, c, wl, wr, sc, rng: tuple(
+            _fake_varlen_bwd(do, q, k, v, o, lse, None, None, None, cq, ck, a, mq, mk, p, s, False, c, wl, wr, sc, False)),
+        "fwd_kvcache": lambda q, kc, vc, k, v, sl, rc, rs, cbi, lp, bt, a, s, c, wl, wr, sc, ri, ns: tuple(
+            _fake_fwd_kvcache(q, kc, vc, k, v, sl, rc, rs, cbi, lp, bt, a, None, s, c, wl, wr, sc, ri, ns)),
+    }
+    try:
+        for name, schema in _FUNCTIONAL_SCHEMAS.items():
+            L.define(f"fa_b200::{name}", schema)
+            L.impl(f"fa_b200::{name}", "CUDA")(impls[name])
+            L.register_fake(f"fa_b200::{name}")(fakes[name])
+        if _ops_registered:
+            for name, fake in (("fwd", _fake_fwd), ("bwd", _fake_bwd), ("varlen_fwd", _fake_varlen_fwd),
+                               ("varlen_bwd", _fake_varlen_bwd), ("fwd_kvcache", _fake_fwd_kvcache)):
+                L.register_fake(f"flash_attn_v100::{name}")(fake)
+    except RuntimeError:
+        return False
+
+    # autograd formulas: the same saved state and gradient calls as the autograd.Function wrappers of the API
+    def fwd_setup(ctx, inputs, output):
+        q, k, v, alibi, p_drop, scale, causal, wl, wr, softcap, _ = inputs
+        out, lse, _, rng = output
+        ctx.save_for_backward(q, k, v, out, lse, rng)
+        ctx.alibi, ctx.opts = alibi, (p_drop, scale, causal, wl, wr, softcap)
+
+    def fwd_backward(ctx, dout, dlse, ddmask, drng):
+        q, k, v, out, lse, rng = ctx.saved_tensors
+        p_drop, scale, causal, wl, wr, softcap = ctx.opts
+        dq, dk, dv, _ = torch.ops.fa_b200.bwd(dout, q, k, v, out, lse, ctx.alibi, p_drop, scale, causal, wl, wr, softcap, rng)
+        return dq, dk, dv, None, None, None, None, None, None, None, None
+
+    def varlen_setup(ctx, inputs, output):
+        q, k, v, cq, ck, bt, alibi, mq, mk, p_drop, scale, causal, wl, wr, softcap, _ = inputs
+        out, lse, _, rng = output
+        ctx.save_for_backward(q, k, v, out, lse, cq, ck, rng)
+        ctx.alibi, ctx.paged, ctx.opts = alibi, bt is not None, (mq, mk, p_drop, scale, causal, wl, wr, softcap)
+
+    def varlen_backward(ctx, dout, dlse, ddmask, drng):
+        if ctx.paged:
+            raise RuntimeError("the backward has no paged-KV form (the reference's varlen_bwd takes no block_table)")
+        q, k, v, out, lse, cq, ck, rng = ctx.saved_tensors
+        mq, mk, p_drop, scale, causal, wl, wr, softcap = ctx.opts
+        dq, dk, dv, _ = torch.ops.fa_b200.varlen_bwd(dout, q, k, v, out, lse, cq, ck, ctx.alibi, mq, mk, p_drop, scale,
+                                                     causal, wl, wr, softcap, rng)
+        return (dq, dk, dv) + (None,) * 13
+
+    L.register_autograd("fa_b200::fwd", fwd_backward, setup_context=fwd_setup)
+    L.register_autograd("fa_b200::varlen_fwd", varlen_backward, setup_context=varlen_setup)
+    _functional_ops_registered = True
+    return True
+
+
+register_functional_ops()

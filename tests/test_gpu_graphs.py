@@ -119,3 +119,59 @@ def test_graph_replay_overlapping_many_eager_launches_on_another_stream(api):
         assert torch.equal(out_static, ref_big), f"replay {rep}: captured forward corrupted by concurrent launches"
         for o in outs:
             assert torch.equal(o, ref_small)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# torch.compile: the reason SURVEY 8(f)3 lists the dispatcher registration
+# ------------------------------------------------------------------------------------------------------------------
+def test_torch_compile_fullgraph_forward_and_backward(api):
+    import torch._dynamo
+
+    torch._dynamo.reset()
+    torch.manual_seed(21)
+    dt = torch.bfloat16
+    q = torch.randn(2, 300, 8, 128, device="cuda", dtype=dt, requires_grad=True)
+    k = torch.randn(2, 300, 2, 128, device="cuda", dtype=dt, requires_grad=True)
+    v = torch.randn(2, 300, 2, 128, device="cuda", dtype=dt, requires_grad=True)
+    w = torch.randn(128, 128, device="cuda", dtype=dt)
+
+    def block(q, k, v):
+        o = api.flash_attn_func(q * 1.0, k, v, causal=True)  # surrounded by ordinary torch ops
+        return (o @ w).float().square().mean()
+
+    compiled = torch.compile(block, fullgraph=True)  # fullgraph: any graph break is an error
+    loss_c = compiled(q, k, v)
+    gc = torch.autograd.grad(loss_c, (q, k, v))
+    loss_e = block(q, k, v)
+    ge = torch.autograd.grad(loss_e, (q, k, v))
+    assert torch.allclose(loss_c, loss_e, rtol=1e-3, atol=1e-5)
+    for a, b in zip(gc, ge):
+        assert (a.float() - b.float()).abs().max().item() <= 2e-2 * max(b.float().abs().max().item(), 1e-6) + 1e-6
+
+
+def test_torch_compile_fullgraph_varlen_and_kvcache(api):
+    import torch._dynamo
+
+    torch._dynamo.reset()
+    torch.manual_seed(22)
+    dt = torch.float16
+    lens = [37, 200, 1, 129]
+    cu = torch.tensor([0, 37, 237, 238, 367], dtype=torch.int32, device="cuda")
+    q = torch.randn(sum(lens), 4, 64, device="cuda", dtype=dt)
+    k = torch.randn(sum(lens), 4, 64, device="cuda", dtype=dt)
+    v = torch.randn(sum(lens), 4, 64, device="cuda", dtype=dt)
+    f = torch.compile(lambda q, k, v: api.flash_attn_varlen_func(q, k, v, cu, cu, 200, 200, causal=True) + 0.0, fullgraph=True)
+    assert torch.equal(f(q, k, v), api.flash_attn_varlen_func(q, k, v, cu, cu, 200, 200, causal=True))
+
+    kc = torch.randn(2, 512, 2, 64, device="cuda", dtype=dt)
+    vc = torch.randn(2, 512, 2, 64, device="cuda", dtype=dt)
+    qd = torch.randn(2, 1, 8, 64, device="cuda", dtype=dt)
+    kn = torch.randn(2, 1, 2, 64, device="cuda", dtype=dt)
+    vn = torch.randn(2, 1, 2, 64, device="cuda", dtype=dt)
+    sl = torch.tensor([100, 7], dtype=torch.int32, device="cuda")
+    g = torch.compile(lambda qd, kc, vc: api.flash_attn_with_kvcache(qd, kc, vc, kn, vn, cache_seqlens=sl, causal=True) * 1.0,
+                      fullgraph=True)
+    kc1, vc1, kc2, vc2 = kc.clone(), vc.clone(), kc.clone(), vc.clone()
+    out_c = g(qd, kc1, vc1)
+    out_e = api.flash_attn_with_kvcache(qd, kc2, vc2, kn, vn, cache_seqlens=sl, causal=True)
+    assert torch.equal(out_c, out_e) and torch.equal(kc1, kc2) and torch.equal(vc1, vc2)  # appended in place in both
