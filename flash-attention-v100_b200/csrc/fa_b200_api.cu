@@ -61,9 +61,54 @@ EncodeTiledFn get_encode_fn() {
 
 // 4-D view (head_dim, heads, rows, batch) of a 16-bit tensor with unit head_dim stride;
 // box = 64 x 1 x 128 x 1 with the 128-byte swizzle the UMMA descriptors expect.
+// Encoded maps are cached per thread, keyed by everything that goes into them: a serving / training loop calls
+// with the same buffers and shapes over and over, and cuTensorMapEncodeTiled is ~1 us of driver time per operand
+// (three per forward call, nine per backward) -- a third of the host cost of a small call.
+struct TmapKey {
+    const void* ptr;
+    int64_t heads, rows, batch, stride_h, stride_s, stride_b;
+    int dtype, head_dim, box_heads, box_rows;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && heads == o.heads && rows == o.rows && batch == o.batch && stride_h == o.stride_h &&
+               stride_s == o.stride_s && stride_b == o.stride_b && dtype == o.dtype && head_dim == o.head_dim &&
+               box_heads == o.box_heads && box_rows == o.box_rows;
+    }
+};
+struct TmapCache {
+    static constexpr int kEntries = 64;
+    TmapKey key[kEntries];
+    CUtensorMap map[kEntries];
+    bool valid[kEntries] = {};
+};
+thread_local TmapCache g_tmap_cache;
+
+int make_tmap_uncached(CUtensorMap* tm, int dtype, const void* ptr, int head_dim, int64_t heads, int64_t rows,
+                       int64_t batch, int64_t stride_h, int64_t stride_s, int64_t stride_b, const char* name,
+                       int box_heads, int box_rows);
+
 int make_tmap(CUtensorMap* tm, int dtype, const void* ptr, int head_dim, int64_t heads, int64_t rows,
               int64_t batch, int64_t stride_h, int64_t stride_s, int64_t stride_b, const char* name,
               int box_heads = 1, int box_rows = 128) {
+    const TmapKey k{ptr, heads, rows, batch, stride_h, stride_s, stride_b, dtype, head_dim, box_heads, box_rows};
+    uint64_t h = reinterpret_cast<uintptr_t>(ptr) >> 4;
+    h = (h ^ (uint64_t)rows * 0x9E3779B97F4A7C15ull ^ (uint64_t)stride_s * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)box_rows) * 0xFF51AFD7ED558CCDull;
+    const int slot = (int)(h >> 58);  // 64 entries, direct mapped
+    TmapCache& c = g_tmap_cache;
+    if (c.valid[slot] && c.key[slot] == k) {
+        memcpy(tm, &c.map[slot], sizeof(CUtensorMap));
+        return 0;
+    }
+    if (int rc = make_tmap_uncached(tm, dtype, ptr, head_dim, heads, rows, batch, stride_h, stride_s, stride_b, name, box_heads, box_rows))
+        return rc;
+    c.key[slot] = k;
+    memcpy(&c.map[slot], tm, sizeof(CUtensorMap));
+    c.valid[slot] = true;
+    return 0;
+}
+
+int make_tmap_uncached(CUtensorMap* tm, int dtype, const void* ptr, int head_dim, int64_t heads, int64_t rows,
+                       int64_t batch, int64_t stride_h, int64_t stride_s, int64_t stride_b, const char* name,
+                       int box_heads, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(FA_B200_EARCH, "cuTensorMapEncodeTiled is not available from this driver");
     CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s must be 16-byte aligned", name);
@@ -112,8 +157,10 @@ int check_device(int device) {
 // zero-fills the columns in between (the tensor maps carry the real head_dim as their innermost extent).
 int tile_dim(int head_dim) { return head_dim <= 64 ? 64 : head_dim <= 128 ? 128 : 256; }
 
+// `pdl`: launch with programmatic stream serialisation -- the kernel may start while its predecessor on the stream
+// (the kv-cache preparation kernel) is still running and waits for it with griddepcontrol.wait (decode path only).
 template <int D, bool BF16, bool FEAT, bool DECODE = false, bool DROPOUT = false>
-int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) {
+int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream, bool pdl = false) {
     using Cfg = fa::FwdConfig<D>;
     auto kern = fa::fa_fwd_sm100_kernel<D, BF16, FEAT, DECODE, DROPOUT>;
     static std::once_flag once[64];
@@ -124,9 +171,26 @@ int launch_fwd_t(const fa::FwdKernelParams& kp, dim3 grid, cudaStream_t stream) 
         attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(smem)");
-    kern<<<grid, 512, Cfg::kSmemBytes, stream>>>(kp);
+    cudaError_t e;
+    if (pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(512, 1, 1);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, kp);
+    } else {
+        kern<<<grid, 512, Cfg::kSmemBytes, stream>>>(kp);
+        e = cudaSuccess;
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "fa_fwd_sm100_kernel launch");
     return 0;
 }
@@ -216,15 +280,15 @@ int launch_fwd(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, bool
 }
 
 // Decode path: packed-GQA split-KV launch + combine.
-int launch_decode(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, dim3 grid, cudaStream_t stream) {
+int launch_decode(const fa::FwdKernelParams& kp, int real_head_dim, int dtype, dim3 grid, cudaStream_t stream, bool pdl) {
     const bool bf16 = dtype == FA_B200_DTYPE_BF16;
     const int head_dim = tile_dim(real_head_dim);
-    if (head_dim == 128 && bf16) return launch_fwd_t<128, true, false, true>(kp, grid, stream);
-    if (head_dim == 128 && !bf16) return launch_fwd_t<128, false, false, true>(kp, grid, stream);
-    if (head_dim == 64 && bf16) return launch_fwd_t<64, true, false, true>(kp, grid, stream);
-    if (head_dim == 64 && !bf16) return launch_fwd_t<64, false, false, true>(kp, grid, stream);
-    if (head_dim == 256 && bf16) return launch_fwd_t<256, true, false, true>(kp, grid, stream);
-    if (head_dim == 256 && !bf16) return launch_fwd_t<256, false, false, true>(kp, grid, stream);
+    if (head_dim == 128 && bf16) return launch_fwd_t<128, true, false, true>(kp, grid, stream, pdl);
+    if (head_dim == 128 && !bf16) return launch_fwd_t<128, false, false, true>(kp, grid, stream, pdl);
+    if (head_dim == 64 && bf16) return launch_fwd_t<64, true, false, true>(kp, grid, stream, pdl);
+    if (head_dim == 64 && !bf16) return launch_fwd_t<64, false, false, true>(kp, grid, stream, pdl);
+    if (head_dim == 256 && bf16) return launch_fwd_t<256, true, false, true>(kp, grid, stream, pdl);
+    if (head_dim == 256 && !bf16) return launch_fwd_t<256, false, false, true>(kp, grid, stream, pdl);
     return fail(FA_B200_EUNSUPPORTED, "head_dim %d is not built", head_dim);
 }
 
@@ -234,8 +298,21 @@ int launch_combine(const fa::FwdKernelParams& kp, const fa_b200_params_t* p, cud
     const dim3 grid((unsigned)((rows + warps - 1) / warps));
     uint16_t* out = static_cast<uint16_t*>(p->out);
     const bool bf16 = p->dtype == FA_B200_DTYPE_BF16;
+    // launched with programmatic stream serialisation: it starts while the decode kernel drains and waits for it
+    // with griddepcontrol.wait
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(warps * 32, 1, 1);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaSuccess;
 #define FA_COMBINE(DD, BB)                                                                                   \
-    fa::fa_combine_kernel<DD, BB><<<grid, warps * 32, 0, stream>>>(kp.o_partial, kp.lse_partial, out, p->lse, \
+    le = cudaLaunchKernelEx(&cfg, fa::fa_combine_kernel<DD, BB>, (const float*)kp.o_partial, (const float*)kp.lse_partial, out, p->lse, \
         kp.num_splits, p->batch, p->num_heads, p->seqlen_q, p->o_stride_b, p->o_stride_s, p->o_stride_h, p->head_dim)
     if (tile_dim(p->head_dim) == 256 && bf16) FA_COMBINE(256, true);
     else if (tile_dim(p->head_dim) == 256) FA_COMBINE(256, false);
@@ -245,7 +322,7 @@ int launch_combine(const fa::FwdKernelParams& kp, const fa_b200_params_t* p, cud
     else FA_COMBINE(64, false);
 #undef FA_COMBINE
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = le != cudaSuccess ? le : cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "fa_combine_kernel launch");
     return 0;
 }
@@ -671,10 +748,11 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
     if (wr >= p->seqlen_k) wr = -1;
     const bool bf16 = p->dtype == FA_B200_DTYPE_BF16;
 
-    // 1. append (+ RoPE on K), once per kv head
+    // 1. append (+ RoPE on K), once per kv head; 2. RoPE on Q into the workspace -- ONE launch when both are needed
+    fa::AppendParams ap;
+    memset(&ap, 0, sizeof(ap));
+    int64_t prep_total = 0;
     if (has_new) {
-        fa::AppendParams ap;
-        memset(&ap, 0, sizeof(ap));
         ap.k_new = static_cast<const uint16_t*>(p->k_new);
         ap.v_new = static_cast<const uint16_t*>(p->v_new);
         ap.k_cache = static_cast<uint16_t*>(const_cast<void*>(p->k));
@@ -694,16 +772,8 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
         ap.interleaved = p->rotary_interleaved;
         ap.block_table_stride = p->block_table_stride;
         ap.page_size = p->page_size;
-        const int64_t total = (int64_t)p->batch * p->seqlen_new * p->num_heads_k * (p->head_dim / 8);
-        const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-        if (bf16) fa::kv_append_kernel<true><<<blocks, 256, 0, stream>>>(ap);
-        else fa::kv_append_kernel<false><<<blocks, 256, 0, stream>>>(ap);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return cuda_fail(e, "kv_append_kernel launch");
+        prep_total = (int64_t)p->batch * p->seqlen_new * p->num_heads_k * (p->head_dim / 8);
     }
-
-    // 2. RoPE on Q into the workspace
     const void* q_ptr = p->q;
     int64_t q_sb = p->q_stride_b, q_ss = p->q_stride_s, q_sh = p->q_stride_h;
     char* ws = static_cast<char*>(p->workspace);
@@ -725,18 +795,27 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
         rp.interleaved = p->rotary_interleaved;
         rp.per_row_pos = (causal || wl >= 0 || wr >= 0) ? 1 : 0;
         const int64_t total = (int64_t)p->batch * p->seqlen_q * p->num_heads * (p->head_dim / 8);
-        const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-        if (bf16) fa::q_rotary_kernel<true><<<blocks, 256, 0, stream>>>(rp);
-        else fa::q_rotary_kernel<false><<<blocks, 256, 0, stream>>>(rp);
+        if (total > prep_total) prep_total = total;
+        const int blocks = (int)((prep_total + 255) / 256 < 148 * 8 ? (prep_total + 255) / 256 : 148 * 8);
+        // rotary implies has_new (checked above): append + RoPE(K) + RoPE(Q) in one launch
+        if (bf16) fa::kv_prep_kernel<true><<<blocks, 256, 0, stream>>>(ap, rp);
+        else fa::kv_prep_kernel<false><<<blocks, 256, 0, stream>>>(ap, rp);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return cuda_fail(e, "q_rotary_kernel launch");
+        if (e != cudaSuccess) return cuda_fail(e, "kv_prep_kernel launch");
         q_ptr = ws;
         q_sh = p->head_dim;
         q_ss = (int64_t)p->num_heads * p->head_dim;
         q_sb = (int64_t)p->seqlen_q * q_ss;
         ws += qbytes;
         ws_left -= qbytes;
+    } else if (has_new) {
+        const int blocks = (int)((prep_total + 255) / 256 < 148 * 8 ? (prep_total + 255) / 256 : 148 * 8);
+        if (bf16) fa::kv_append_kernel<true><<<blocks, 256, 0, stream>>>(ap);
+        else fa::kv_append_kernel<false><<<blocks, 256, 0, stream>>>(ap);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "kv_append_kernel launch");
     }
 
     // 3. attention over the cache: the tcgen05 kernel reading the (paged) cache through TMA
@@ -774,7 +853,8 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
             kp.lse_partial = reinterpret_cast<float*>(ws + obytes);
         }
         dim3 grid(kp.num_splits, p->num_heads_k, p->batch);
-        if (int rc = launch_decode(kp, p->head_dim, p->dtype, grid, stream)) return rc;
+        // programmatic dependent launch behind the preparation kernel (when there is one)
+        if (int rc = launch_decode(kp, p->head_dim, p->dtype, grid, stream, has_new)) return rc;
         if (kp.num_splits > 1) return launch_combine(kp, p, stream);
         return 0;
     }

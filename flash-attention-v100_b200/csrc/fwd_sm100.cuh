@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstdint>
 
+#include "kvcache_prep.cuh"
 #include "ptx_sm100.cuh"
 #include "umma_issue_gen.cuh"
 
@@ -421,6 +422,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if constexpr (DECODE) {
+        // programmatic dependent launch: everything above overlapped the kv-cache preparation kernel; its writes
+        // (appended K/V rows, the rotated Q) are visible after the wait. The combine kernel may start likewise.
+        pdl_wait_primary();
+        pdl_launch_dependents();
+    }
 
     // Consumer side of the scheduler: k-th work id of this CTA (>= total_work means "no more work").
     auto get_work = [&](int k) -> int {
@@ -1054,6 +1061,7 @@ __global__ void fa_combine_kernel(const float* __restrict__ o_partial, const flo
     const int lane = threadIdx.x & 31;
     const int64_t rows = (int64_t)batch * heads * seqlen_q;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_wait_primary();  // launched with programmatic stream serialisation behind the decode kernel
     if (row >= rows) return;
     const int pos = row % seqlen_q, h = (row / seqlen_q) % heads, b = row / ((int64_t)seqlen_q * heads);
     float mx = -INFINITY;

@@ -78,9 +78,16 @@ struct AppendParams {
     int block_table_stride, page_size;
 };
 
+// Programmatic dependent launch (sm_90+): the attention kernel that follows on the stream is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so it may start (and run its set-up: barrier init, TMEM
+// allocation, tensor-map prefetch) while this kernel is still running; it executes griddepcontrol.wait before it
+// touches anything written here. Both instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // one thread per 8 consecutive elements of one (batch, new row, kv head)
 template <bool BF16>
-__global__ void kv_append_kernel(const AppendParams p) {
+__device__ __forceinline__ void kv_append_body(const AppendParams& p) {
     const int chunks = p.head_dim / 8;
     const int64_t total = (int64_t)p.batch * p.seqlen_new * p.heads_k * chunks;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -135,7 +142,7 @@ struct QRotaryParams {
 };
 
 template <bool BF16>
-__global__ void q_rotary_kernel(const QRotaryParams p) {
+__device__ __forceinline__ void q_rotary_body(const QRotaryParams& p) {
     const int chunks = p.head_dim / 8;
     const int64_t total = (int64_t)p.batch * p.seqlen_q * p.heads * chunks;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -162,6 +169,25 @@ __global__ void q_rotary_kernel(const QRotaryParams p) {
             *reinterpret_cast<uint4*>(dst + d0) = *reinterpret_cast<const uint4*>(src + d0);
         }
     }
+}
+
+template <bool BF16>
+__global__ void kv_append_kernel(const AppendParams p) {
+    pdl_launch_dependents();
+    kv_append_body<BF16>(p);
+}
+template <bool BF16>
+__global__ void q_rotary_kernel(const QRotaryParams p) {
+    pdl_launch_dependents();
+    q_rotary_body<BF16>(p);
+}
+// append + RoPE(K) and RoPE(Q) in ONE launch (a decode step needs both; each launch costs the host ~2.5 us and the
+// GPU a dependent-launch gap)
+template <bool BF16>
+__global__ void kv_prep_kernel(const AppendParams ap, const QRotaryParams rp) {
+    pdl_launch_dependents();
+    kv_append_body<BF16>(ap);
+    q_rotary_body<BF16>(rp);
 }
 
 }  // namespace fa

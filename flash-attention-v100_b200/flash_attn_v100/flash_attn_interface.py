@@ -170,6 +170,11 @@ def flash_attn_func(
     try:
         grad = torch.is_grad_enabled()
         if not (grad and (q.requires_grad or k.requires_grad or v.requires_grad)):
+            if dropout_p == 0.0 and alibi_slopes is None and not return_attn_probs:
+                # the steady-state inference call: validated once per signature, then a pre-filled parameter block
+                out = flash_attn_v100_cuda.fwd_dense_fast(q, k, v, softmax_scale, causal, window_size[0], window_size[1], softcap)
+                if out is not None:
+                    return out
             # nothing to record: call the forward directly (autograd.Function.apply costs ~10 us per call, which is
             # most of a small problem's latency); same code path, same results
             return FlashAttnFunc.forward(_NO_CTX, q, k, v, dropout_p, softmax_scale, causal, window_size, softcap,

@@ -295,6 +295,158 @@ def fwd(q, k, v, out_, alibi_slopes_, p_dropout, softmax_scale, is_causal, windo
     return [out, lse, dmask, rng_state]
 
 
+# --------------------------------------------------------------------------------------
+# Dense forward, lean path for the steady state of an inference loop: same call, same kernel, but everything that
+# depends only on shapes / strides / dtypes / options is validated ONCE per distinct signature and kept as a
+# pre-filled parameter block; a repeat call allocates `out`, patches four pointers and enters the C ABI.
+# (tools/host_overhead.py: the general path above costs ~26 us of Python per call on top of the 6 us C call -- more
+# than the 12 us the GPU needs for BASELINE config 1.) Per-thread, so concurrent callers never share a block.
+# --------------------------------------------------------------------------------------
+import threading  # noqa: E402
+
+_fast_tls = threading.local()
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _fast_entry(q, k, v, softmax_scale, causal, wl, wr, softcap):
+    """Validated parameter block for this signature, or False if the lean path does not apply (the general path
+    then handles -- or rejects -- the call with its usual messages)."""
+    if q.dim() != 4 or k.dim() != 4 or v.shape != k.shape or not (q.is_cuda and k.is_cuda and v.is_cuda):
+        return False
+    if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype or v.dtype != q.dtype:
+        return False
+    if k.device != q.device or v.device != q.device:
+        return False
+    B, M, H, D = q.shape
+    N, Hk = k.shape[1], k.shape[2]
+    if min(B, M, N, H, Hk) <= 0 or k.shape[0] != B or k.shape[3] != D or H % Hk or D % 8 or D > 256:
+        return False
+    for t in (q, k, v):
+        if t.stride(-1) != 1 or any(n != 1 and (s <= 0 or s % 8) for n, s in zip(t.shape[:-1], t.stride()[:-1])):
+            return False
+    lib = load_library()
+    p = FaB200Params()
+    p.struct_bytes = ctypes.sizeof(FaB200Params)
+    p.dtype = FA_B200_DTYPE_FP16 if q.dtype == torch.float16 else FA_B200_DTYPE_BF16
+    p.device = q.device.index if q.device.index is not None else torch.cuda.current_device()
+    p.batch, p.seqlen_q, p.seqlen_k, p.num_heads, p.num_heads_k, p.head_dim = B, M, N, H, Hk, D
+    p.q_stride_b, p.q_stride_s, p.q_stride_h = q.stride(0), q.stride(1), q.stride(2)
+    p.k_stride_b, p.k_stride_s, p.k_stride_h = k.stride(0), k.stride(1), k.stride(2)
+    p.v_stride_b, p.v_stride_s, p.v_stride_h = v.stride(0), v.stride(1), v.stride(2)
+    p.o_stride_b, p.o_stride_s, p.o_stride_h = M * H * D, H * D, D  # a fresh contiguous (B, M, H, D) tensor
+    p.softmax_scale = float(D ** -0.5 if softmax_scale is None else softmax_scale)
+    p.softcap = float(softcap)
+    p.is_causal, p.window_left, p.window_right = int(bool(causal)), int(wl), int(wr)
+    return (p, ctypes.byref(p), lib.fa_b200_fwd, (B, H, M), (B, M, H, D), p.device)
+
+
+def fwd_dense_fast(q, k, v, softmax_scale, causal, wl, wr, softcap):
+    """flash_attn_func(q, k, v, softmax_scale=, causal=, window_size=, softcap=) on (B, S, H, D) tensors when nothing
+    else is asked for (no dropout / ALiBi / returned statistics / autograd). Returns `out`, or None when the call is
+    not eligible and must take the general path."""
+    cache = getattr(_fast_tls, "cache", None)
+    if cache is None:
+        cache = _fast_tls.cache = {}
+    key = (q.shape, k.shape, v.shape, q.stride(), k.stride(), v.stride(), q.dtype, q.device, softmax_scale, causal, wl, wr, softcap)
+    ent = cache.get(key)
+    if ent is None:
+        if len(cache) > 256:
+            cache.clear()
+        ent = cache[key] = _fast_entry(q, k, v, softmax_scale, causal, wl, wr, softcap)
+    if ent is False:
+        return None
+    p, ref, fn, lshape, oshape, dev = ent
+    qp, kp, vp = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    if (qp | kp | vp) & 15:
+        return None
+    out = torch.empty(oshape, dtype=q.dtype, device=q.device)
+    # the LSE is allocated per call even though nobody receives it here: a cached scratch buffer would be baked into
+    # captured CUDA graphs and could not be dropped from the cache safely
+    lse = torch.empty(lshape, dtype=torch.float32, device=q.device)
+    p.q, p.k, p.v, p.out, p.lse = qp, kp, vp, out.data_ptr(), lse.data_ptr()
+    stream = _raw_stream(dev) if _raw_stream is not None else torch.cuda.current_stream(q.device).cuda_stream
+    rc = fn(ref, stream)
+    if rc != 0:
+        msg = load_library().fa_b200_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"fa_b200_fwd failed ({rc}): {msg}")
+    return out
+
+
+def _sig(t):
+    return None if t is None else (t.shape, t.stride(), t.dtype)
+
+
+def fwd_kvcache_fast(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_, cache_batch_idx_, leftpad_k_,
+                     block_table_, alibi_slopes_, softmax_scale, is_causal, window_left, window_right, softcap,
+                     is_rotary_interleaved, num_splits):
+    """The lean path of `fwd_kvcache` for a decode loop: the first call with a given signature (shapes, strides,
+    dtypes, which optional tensors are present, scalar options) goes through the general path once -- so every check and
+    error message is the reference's -- and its filled parameter block is kept; repeat calls allocate out / lse /
+    workspace, patch the pointers and enter the C ABI. Returns [out, lse], or None if the signature is not cached
+    yet / not eligible (the caller then takes the general path)."""
+    cache = getattr(_fast_tls, "kv_cache", None)
+    if cache is None:
+        cache = _fast_tls.kv_cache = {}
+    key = (_sig(q), _sig(kcache), _sig(vcache), _sig(k_), _sig(v_), _sig(seqlens_k_), _sig(rotary_cos_), _sig(rotary_sin_),
+           _sig(cache_batch_idx_), _sig(leftpad_k_), _sig(block_table_), _sig(alibi_slopes_), q.device, softmax_scale,
+           is_causal, window_left, window_right, softcap, is_rotary_interleaved, num_splits)
+    ent = cache.get(key)
+    if ent is None:
+        return None
+    p, ref, fn, ws_fn, ws_bytes, oshape, lshape, dev = ent
+    ptrs = [q.data_ptr(), kcache.data_ptr(), vcache.data_ptr()]
+    p.q, p.k, p.v = ptrs
+    if k_ is not None:
+        p.k_new, p.v_new = k_.data_ptr(), v_.data_ptr()
+        ptrs += [p.k_new, p.v_new]
+    acc = 0
+    for x in ptrs:
+        acc |= x
+    if acc & 15:
+        return None
+    if seqlens_k_ is not None:
+        p.cache_seqlens = seqlens_k_.data_ptr()
+    if cache_batch_idx_ is not None:
+        p.cache_batch_idx = cache_batch_idx_.data_ptr()
+    if leftpad_k_ is not None:
+        p.cache_leftpad = leftpad_k_.data_ptr()
+    if rotary_cos_ is not None:
+        p.rotary_cos, p.rotary_sin = rotary_cos_.data_ptr(), rotary_sin_.data_ptr()
+    if block_table_ is not None:
+        p.block_table = block_table_.data_ptr()
+    if alibi_slopes_ is not None:
+        p.alibi_slopes = alibi_slopes_.data_ptr()
+    out = torch.empty(oshape, dtype=q.dtype, device=q.device)
+    lse = torch.empty(lshape, dtype=torch.float32, device=q.device)
+    p.out, p.lse = out.data_ptr(), lse.data_ptr()
+    if ws_bytes:
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
+        p.workspace = ws.data_ptr()
+    stream = _raw_stream(dev) if _raw_stream is not None else torch.cuda.current_stream(q.device).cuda_stream
+    rc = fn(ref, stream)
+    if rc != 0:
+        msg = load_library().fa_b200_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"fa_b200_kvcache_fwd failed ({rc}): {msg}")
+    return [out, lse]
+
+
+def _remember_kvcache_signature(p, args):
+    """Called by the general path after a successful call that used only directly consumable tensors."""
+    (q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_, cache_batch_idx_, leftpad_k_, block_table_,
+     alibi_slopes_, softmax_scale, is_causal, window_left, window_right, softcap, is_rotary_interleaved, num_splits) = args
+    cache = getattr(_fast_tls, "kv_cache", None)
+    if cache is None:
+        cache = _fast_tls.kv_cache = {}
+    if len(cache) > 256:
+        cache.clear()
+    key = (_sig(q), _sig(kcache), _sig(vcache), _sig(k_), _sig(v_), _sig(seqlens_k_), _sig(rotary_cos_), _sig(rotary_sin_),
+           _sig(cache_batch_idx_), _sig(leftpad_k_), _sig(block_table_), _sig(alibi_slopes_), q.device, softmax_scale,
+           is_causal, window_left, window_right, softcap, is_rotary_interleaved, num_splits)
+    lib = load_library()
+    B, Sq, H, D = q.shape
+    cache[key] = (p, ctypes.byref(p), lib.fa_b200_kvcache_fwd, None, int(p.workspace_bytes), (B, Sq, H, D), (B, H, Sq), int(p.device))
+
+
 # ======================================================================================
 # varlen:  replaces flash_attention_varlen_forward (reference kernel/fused_mha_forward_varlen.cu:371-566)
 # ======================================================================================
@@ -400,6 +552,13 @@ def varlen_fwd(q, k, v, out_, cu_seqlens_q, cu_seqlens_k, seqused_k_, leftpad_k_
 def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_, cache_batch_idx_, leftpad_k_,
                 block_table_, alibi_slopes_, out_, softmax_scale, is_causal, window_left, window_right, softcap,
                 is_rotary_interleaved, num_splits) -> List[torch.Tensor]:
+    _fast_args = (q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_, cache_batch_idx_, leftpad_k_,
+                  block_table_, alibi_slopes_, softmax_scale, is_causal, window_left, window_right, softcap,
+                  is_rotary_interleaved, num_splits)
+    if out_ is None:
+        res = fwd_kvcache_fast(*_fast_args)  # a signature seen (and fully validated) before
+        if res is not None:
+            return res
     _check(q.is_cuda and kcache.is_cuda and vcache.is_cuda, "q, kcache, vcache must be on CUDA")
     dt = _dtype_code(q)
     _check(kcache.dtype == q.dtype and vcache.dtype == q.dtype, "kcache/vcache must have the same dtype as q")
@@ -509,6 +668,10 @@ def fwd_kvcache(q, kcache, vcache, k_, v_, seqlens_k_, rotary_cos_, rotary_sin_,
     if not direct and out_ is not None:
         out_.copy_(out)
         out = out_
+    if out_ is None and qa is q and (k_ is None or (k_ is _fast_args[3] and v_ is _fast_args[4])):
+        # every tensor was consumed in place (no .contiguous() copies): repeat calls with this signature can skip
+        # the validation and fill-in above
+        _remember_kvcache_signature(p, _fast_args)
     return [out, lse]
 
 
