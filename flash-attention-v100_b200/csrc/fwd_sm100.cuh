@@ -736,13 +736,32 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
 
                 if constexpr (FEAT) {
                     // reference order (include/mat_mul.h:111-117): scale, ALiBi, then softcap
-                    const int rel0 = i_glob + w.off - j0;
+                    const int rel0 = i_glob + w.off - j0;  // column of this tile that sits on the row's diagonal
+                    // ALiBi alone is AFFINE in the column index on every tile that does not straddle the diagonal of any
+                    // row of the warp: -slope |rel0 - c| = -/+ slope (rel0 - c). Score, scale and bias then fold into one
+                    // packed FMA per pair plus one immediate-operand FMA per element for the bias (a * c + b0, c a
+                    // compile-time constant): ~2.5 instructions per pair instead of ~12 (the general path below converts
+                    // an integer per element). Only the diagonal tiles of a causal walk take the general path.
+                    const bool affine = p.softcap <= 0.f;
+                    const bool all_left = affine && __all_sync(0xffffffffu, rel0 >= BN - 1);  // every column <= diagonal
+                    const bool all_right = affine && __all_sync(0xffffffffu, rel0 <= 0);      // every column >= diagonal
+                    if (all_left || all_right) {
+                        const float a = (all_left ? slope : -slope) * kLog2e;
+                        const float b0 = -a * (float)rel0;
+                        const float s2 = p.scale * kLog2e;
 #pragma unroll
-                    for (int c = 0; c < BN; ++c) {
-                        float u = v[c] * p.scale;
-                        u -= slope * fabsf((float)(rel0 - c));
-                        if (p.softcap > 0.f) u = p.softcap * tanh_approx(u * inv_cap);
-                        v[c] = u * kLog2e;
+                        for (int c = 0; c < BN; c += 2) {
+                            const float bias0 = fmaf(a, (float)c, b0), bias1 = fmaf(a, (float)(c + 1), b0);
+                            fma2(v[c], v[c + 1], s2, s2, bias0, bias1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BN; ++c) {
+                            float u = v[c] * p.scale;
+                            u -= slope * fabsf((float)(rel0 - c));
+                            if (p.softcap > 0.f) u = p.softcap * tanh_approx(u * inv_cap);
+                            v[c] = u * kLog2e;
+                        }
                     }
                 }
                 if (any_mask) {
