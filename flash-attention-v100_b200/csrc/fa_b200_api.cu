@@ -584,6 +584,14 @@ __attribute__((visibility("default"))) int fa_b200_debug_set_trace(void* dev_ptr
 }
 #endif
 
+#ifdef FA_WAIT_LOG
+// debug builds only: zero-copy pinned host buffer of 256 blocks x 16 warps x uint64 (ptx_sm100.cuh: fa_wait_log)
+__attribute__((visibility("default"))) int fa_b200_debug_set_wait_log(void* host_mapped_ptr) {
+    unsigned long long* p = static_cast<unsigned long long*>(host_mapped_ptr);
+    return (int)cudaMemcpyToSymbol(fa::g_fa_wait_log, &p, sizeof(p));
+}
+#endif
+
 // Tests only: device pointer to two zero-initialised 64-bit counters ([0] softmax rows that crossed the lazy-rescale
 // threshold, [1] accumulator rescales executed), or NULL to switch counting off. Not part of the drop-in surface.
 __attribute__((visibility("default"))) int fa_b200_debug_set_counters(void* dev_ptr) {

@@ -139,6 +139,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units; O is rescaled only whe
 #ifndef FA_SPLIT_P
 #define FA_SPLIT_P 1     // signal the MMA warp after 3/4 of P so P V starts before the last quarter
 #endif
+#ifndef FA_SHARED_S
+#define FA_SHARED_S 1    // one S buffer shared by both stages + a private P buffer per stage (see "TMEM map"): the next
+#endif                   // Q K^T of a stage no longer waits for that stage's softmax -> P V chain
 #ifndef FA_LD_OVERLAP
 #define FA_LD_OVERLAP 0  // softmax: split the S load so the row max of the first half overlaps the second half's load
 #endif
@@ -180,22 +183,30 @@ struct FwdConfig {
     static constexpr int kKvStages = (D == 256) ? 2 : (D == 128) ? 4 : 6;
     static constexpr int kSmemQ = kSplitD ? kTileBytes : 2 * kTileBytes;
     static constexpr int kSmemKV = kKvStages * kTileBytes;
-    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1 + 2 + 1 + 1;
+    static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1 + 2 + 1 + 1 + 2 + 2;
     static constexpr int kOffBars = kSmemQ + kSmemKV;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
     static constexpr int kOffScale = (kOffTmemPtr + 16 + 15) & ~15;
-    static constexpr int kOffRowSum = kOffScale + 2 * 128 * 4;      // [item parity][stage][128]
+    static constexpr int kOffRowSum = kOffScale + 2 * 2 * 128 * 4;  // (sScale: [tile parity][stage][128]) [item parity][stage][128]
     static constexpr int kOffRowMax = kOffRowSum + 2 * 2 * 128 * 4;  // [item parity][stage][128]
     static constexpr int kOffSched = kOffRowMax + 2 * 2 * 128 * 4;   // int[2] work ids (+ 8 bytes of padding)
     static constexpr int kOffClc = kOffSched + 16;                   // 16-byte cluster-launch-control response
     static constexpr int kSmemUsed = kOffClc + 16;
     static constexpr int kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
-    static constexpr int kTmemS0 = 0, kTmemS1 = 128, kTmemO0 = 256, kTmemO1 = 256 + kDO;
-    static constexpr int kTmemPOff = 64;
+    // TMEM map. FA_SHARED_S = 0: S0 [0,128) S1 [128,256), P_s = upper half of S_s.
+    // FA_SHARED_S = 1: ONE S buffer [0,128) that the stages use in turn (a softmax warp copies its S tile to registers
+    // within ~200 clocks, after which the buffer is free for the other stage's next Q K^T) and a private P buffer per
+    // stage, P0 [128,192) P1 [192,256). P_s(j) no longer shares columns with S_s(j+1), so Q K^T(j+1) of a stage is
+    // issued BEFORE P V(j) of that stage and is usually complete by the time the stage's softmax warps finish tile j:
+    // they go from tile to tile without waiting for the tensor pipe (round 1: one third of their time was that wait).
+    static constexpr bool kSharedS = FA_SHARED_S != 0;
+    static constexpr int kTmemS0 = 0, kTmemS1 = kSharedS ? 0 : 128, kTmemO0 = 256, kTmemO1 = 256 + kDO;
+    static constexpr int kTmemP0 = kSharedS ? 128 : 64, kTmemP1 = kSharedS ? 192 : 128 + 64;
+    static constexpr int kTmemPOff = 64;  // forward v2 (fwd2_sm100.cuh): P_i = upper half of S_i
     // Early left half of S: two N=64 MMAs read the Q tile from shared memory twice, and an SS-form 128x128x16 MMA
     // already needs the full 128 B/clk of shared-memory bandwidth -- measured -10 % at head_dim 128 (tensor pipe is
     // the bottleneck there), +7 % at head_dim 64 (the softmax is, and the pipe has slack).
-    static constexpr bool kEarlyQK = FA_EARLY_QK && (D == 64);
+    static constexpr bool kEarlyQK = FA_EARLY_QK && (D == 64) && !kSharedS;
 };
 
 // Per-sequence geometry shared by every role.
@@ -368,7 +379,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     constexpr int kB0 = 2 + 2 * KV;
     auto bar_s_full = [&](int s) { return bars + 8 * (kB0 + s); };       // MMA -> softmax: S_s ready
     auto bar_p_full = [&](int s) { return bars + 8 * (kB0 + 2 + s); };   // softmax+correction -> MMA
-    auto bar_stats = [&](int s) { return bars + 8 * (kB0 + 4 + s); };    // softmax -> correction: scale
+    // softmax -> correction: scale; double-buffered by tile parity (the softmax of a stage may publish tile j+1 before
+    // the correction warps have looked at tile j: they serve both stages in turn)
+    auto bar_stats = [&](int s, int par) { return bars + 8 * (par ? kB0 + 26 + s : kB0 + 4 + s); };
     auto bar_o_full = [&](int s) { return bars + 8 * (kB0 + 6 + s); };   // MMA -> correction: O_s final
     auto bar_p_last = [&](int s) { return bars + 8 * (kB0 + 8 + s); };   // softmax -> MMA: last 1/4 of P
     auto bar_final = [&](int s, int b) { return bars + 8 * (kB0 + 10 + 2 * s + b); };  // softmax -> corr.: l, m
@@ -379,7 +392,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     auto bar_s_loaded = [&](int s) { return bars + 8 * (kB0 + 20 + s); };  // softmax -> MMA: S_s is in registers
     const uint32_t bar_clc = bars + 8 * (kB0 + 22);  // launch unit -> loader: cancellation response landed
     const uint32_t bar_done = bars + 8 * (kB0 + 23);  // role warps -> watchdog: this warp has left its loop
-    static_assert(kB0 + 24 <= Cfg::kNumBars, "barrier table too small");
+    auto bar_p_free = [&](int s) { return bars + 8 * (kB0 + 24 + s); };  // MMA -> softmax, correction: P V_s of a tile done
+    const uint32_t bar_sx_free = bar_s_loaded(0);  // shared-S mode: softmax (either stage) -> MMA: the S buffer is in registers
+    static_assert(kB0 + 28 <= Cfg::kNumBars, "barrier table too small");
     const uint32_t sClc = sbase + Cfg::kOffClc;
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + Cfg::kOffTmemPtr);
     float* sScale = reinterpret_cast<float*>(sgen + Cfg::kOffScale);
@@ -395,12 +410,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             mbar_init(bar_q_full(s), 1);
             mbar_init(bar_s_full(s), 1);
             mbar_init(bar_p_full(s), 8);  // 4 softmax warps + 4 correction warps
-            mbar_init(bar_stats(s), 4);
+            mbar_init(bar_stats(s, 0), 4);
+            mbar_init(bar_stats(s, 1), 4);
             mbar_init(bar_o_full(s), 1);
             mbar_init(bar_p_last(s), 4);
             mbar_init(bar_s_loaded(s), 4);
             mbar_init(bar_final(s, 0), 4);
             mbar_init(bar_final(s, 1), 4);
+            mbar_init(bar_p_free(s), 1);
             mbar_init(bar_sched_full(s), 1);
             mbar_init(bar_sched_empty(s), 14);  // MMA warp + 8 softmax + 4 correction warps + V sanitiser
         }
@@ -591,19 +608,23 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         auto slot_addr = [&](int r) { return sKV + (r % KV) * Cfg::kTileBytes; };
         auto wait_full = [&](int r) { mbar_wait(bar_kv_full(r % KV), (r / KV) & 1); };
 
+        const uint32_t tPs[2] = {tmem_base + Cfg::kTmemP0, tmem_base + Cfg::kTmemP1};
         int ring = 0;           // ring entries consumed by earlier items
         int ka = 0;             // items with work so far
         int kfix = 0;           // items with a ragged tail so far
         int steps[2] = {0, 0};  // softmax steps of earlier items, per stage (barrier phase bookkeeping)
+        int sx_uses = 0;        // shared-S mode: Q K^T tiles written into the S buffer so far
         for (int k = 0;; ++k) {
             const int id = get_work(k);
             if (id >= total_work) break;
             const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
             if (w.n_tiles <= 0) continue;
             mbar_wait(bar_q_full(0), ka & 1);
-            // Issue order per iteration: PV0(it-1) QK0(it) PV1(it-1) QK1(it). tcgen05 ops execute in issue
-            // order, so S_s(it) may overwrite the columns P_s(it-1) lives in without a barrier, and the
-            // first QK^T of the next item may follow the last P V of this one directly.
+            // Issue order per iteration. Separate S buffers: PV0(it-1) QK0(it) PV1(it-1) QK1(it) -- tcgen05 ops execute in
+            // issue order, so S_s(it) may overwrite the columns P_s(it-1) lives in without a barrier. Shared S buffer:
+            // QK0(it) PV0(it-1) QK1(it) PV1(it-1) -- a Q K^T only waits until the previous S tile (the other stage's, as a
+            // rule) has been copied to registers, so it runs while its own stage is still busy with the tile before.
+            // Either way the first QK^T of the next item may follow the last P V of this one directly.
             for (int it = 0; it <= w.n_tiles; ++it) {
                 if (it > 0) wait_full(ring + 2 * it - 1);
                 if (it == 1 && w.ragged_tail) mbar_wait(bar_vfix, kfix & 1);  // V rows past seqlen_k are zero now
@@ -613,10 +634,22 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 for (int s = 0; s < 2; ++s) {
                     const bool do_pv = it > 0 && (it - 1) >= w.it_lo[s] && (it - 1) < w.it_hi[s];
                     const bool do_qk = it < w.n_tiles && it >= w.it_lo[s] && it < w.it_hi[s];
+                    auto qk = [&]() {
+                        if (Cfg::kSharedS) {  // the S tile written before this one sits in its owner's registers
+                            if (sx_uses > 0) mbar_wait(bar_sx_free, (sx_uses - 1) & 1);
+                            ++sx_uses;
+                        }
+                        tc_fence_after();
+                        if (Cfg::kEarlyQK && do_pv) issue_qk_half(s, slot_addr(ring + 2 * it), 1);  // left half went ahead
+                        else issue_qk(s, slot_addr(ring + 2 * it));
+                        umma_commit_elect(bar_s_full(s));
+                        FA_TRACE_EV(120 + s);  // MMA: QK_s issued
+                    };
+                    if (Cfg::kSharedS && do_qk) qk();
                     if (do_pv) {
                         const int j = it - 1 - w.it_lo[s];
                         const uint32_t ph = (steps[s] + j) & 1;
-                        const uint32_t tP = tS[s] + Cfg::kTmemPOff;
+                        const uint32_t tP = tPs[s];
                         // split-D: stage s multiplies by its own 128-column half of V (two swizzle blocks further)
                         const uint32_t v_lo = lo_addr(slot_addr(ring + 2 * it - 1) + (SPLIT ? s * 2 * Cfg::kHalfBytes : 0)) | kLoVmn;
                         if (Cfg::kEarlyQK) {
@@ -642,15 +675,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         } else {
                             umma_issue_pv_k0_8(tO[s], tP, v_lo, 0, kDescHi, idesc_pv, j > 0 ? 1u : 0u);
                         }
+                        if (Cfg::kSharedS) umma_commit_elect(bar_p_free(s));  // P_s may be overwritten, O_s rescaled
                         if (it == w.it_hi[s]) umma_commit_elect(bar_o_full(s));
                     }
-                    if (do_qk) {
-                        tc_fence_after();
-                        if (Cfg::kEarlyQK && do_pv) issue_qk_half(s, slot_addr(ring + 2 * it), 1);  // left half went ahead
-                        else issue_qk(s, slot_addr(ring + 2 * it));
-                        umma_commit_elect(bar_s_full(s));
-                        FA_TRACE_EV(120 + s);  // MMA: QK_s issued
-                    }
+                    if (!Cfg::kSharedS && do_qk) qk();
                 }
                 if (it > 0) umma_commit_elect(bar_kv_empty((ring + 2 * it - 1) % KV));
                 if (it < w.n_tiles) umma_commit_elect(bar_kv_empty((ring + 2 * it) % KV));
@@ -671,7 +699,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tmem_base + lane_off + (s == 0 ? Cfg::kTmemS0 : Cfg::kTmemS1);
-        const uint32_t tP = tS + Cfg::kTmemPOff;
+        const uint32_t tP = tmem_base + lane_off + (s == 0 ? Cfg::kTmemP0 : Cfg::kTmemP1);
         const float sl2 = FEAT ? 1.0f : p.scale_log2;
         int steps = 0;  // softmax steps of earlier items (barrier phase bookkeeping)
         int items = 0;  // earlier items in which this stage took part
@@ -720,7 +748,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 const bool need_mask = (j0 + BN > col_hi) || (j0 < col_lo);
                 const bool any_mask = __any_sync(0xffffffffu, need_mask);
                 // FA_LD_OVERLAP: the row max of columns [0,64) runs while columns [64,128) are still on their way
-                const bool split_ld = FA_LD_OVERLAP && !FEAT && !Cfg::kEarlyQK && !any_mask;
+                const bool split_ld = FA_LD_OVERLAP && !FEAT && !Cfg::kEarlyQK && !Cfg::kSharedS && !any_mask;
                 if (split_ld) {
                     tmem_ld_2x32_wait(tS, reinterpret_cast<uint32_t*>(v));
                     tmem_ld_2x32_nowait(tS + 64, reinterpret_cast<uint32_t*>(v + 64));
@@ -728,10 +756,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
                 }
                 FA_TRACE_EV(2);  // softmax: S in registers
-                if (Cfg::kEarlyQK) {
+                if (Cfg::kEarlyQK || Cfg::kSharedS) {  // (shared-S mode: bar_s_loaded(0) is the buffer's "free" barrier)
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_s_loaded(s));
+                    if (lane == 0) mbar_arrive(Cfg::kSharedS ? bar_sx_free : bar_s_loaded(s));
                 }
 
                 if constexpr (FEAT) {
@@ -800,9 +828,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         if (p.dbg_counters) atomicAdd(p.dbg_counters, 1ull);
                     }
                 }
-                sScale[s * BM + row] = acc_scale;
+                const int tpar = (steps + j) & 1;
+                sScale[(tpar * 2 + s) * BM + row] = acc_scale;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_stats(s));
+                if (lane == 0) mbar_arrive(bar_stats(s, tpar));
                 FA_TRACE_EV(3);  // softmax: row max done, stats published
 
                 const float m_used = (m_ref == -INFINITY) ? 0.f : m_ref;
@@ -862,6 +891,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                                 }
                             }
                         }
+                    }
+                    if (Cfg::kSharedS && ch == 0 && steps + j > 0) {
+                        // This stage's softmax runs ahead of its P V: before P_s is overwritten, the P V of the stage's
+                        // previous tile must have read it. Its completion also means the MMA warp consumed the previous
+                        // p_full / p_last phases, so those barriers never get two phases ahead of their waiter.
+                        mbar_wait(bar_p_free(s), (steps + j - 1) & 1);
+                        tc_fence_after();
+                        FA_TRACE_EV(7);  // softmax: previous P V of this stage complete
                     }
                     tmem_st_x16(tP + ch * 16, pk);
                     if (FA_SPLIT_P && ch == BN / 32 - 2) {  // 3/4 of P is on its way: let P V start
@@ -933,9 +970,19 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 for (int s = 0; s < 2; ++s) {
                     if (it < w.it_lo[s] || it >= w.it_hi[s]) continue;
                     const int j = it - w.it_lo[s];
-                    mbar_wait(bar_stats(s), (steps[s] + j) & 1);
+                    const int tpar = (steps[s] + j) & 1;
+                    mbar_wait(bar_stats(s, tpar), ((steps[s] + j) >> 1) & 1);
                     FA_TRACE_EV(200 + s);  // correction: stats observed
-                    const float sc = sScale[s * BM + row];
+                    const float sc = sScale[(tpar * 2 + s) * BM + row];
+                    if (Cfg::kSharedS && steps[s] + j > 0) {
+                        // Shared-S mode: the softmax of a stage publishes the stats of tile j while P V_s(j-1) may not even
+                        // have been issued. Each correction warp therefore waits for P V_s(j-1) to COMPLETE before it
+                        // touches O_s or arrives on p_full for tile j: (a) O_s is not rescaled under a running MMA, and
+                        // (b) p_full has collected all eight arrivals of tile j-1 -- otherwise a correction warp that is a
+                        // tile ahead of a sibling would fill the sibling's slot in the previous phase (found as a hang
+                        // under ncu's SASS-patching passes, which slow the warps of a CTA very unevenly).
+                        mbar_wait(bar_p_free(s), (steps[s] + j - 1) & 1);
+                    }
                     if (j > 0 && __any_sync(0xffffffffu, sc != 1.0f)) {
                         if (p.dbg_counters && lane == 0) atomicAdd(p.dbg_counters + 1, 1ull);
                         tc_fence_after();

@@ -36,7 +36,31 @@ FA_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
 FA_DEVICE void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// -DFA_JITTER: protocol stress build. Every wait and every arrival is preceded, one time in four, by a pseudo-random
+// sleep of up to ~4 us (per warp, per call), which skews the warp roles against each other far beyond anything the
+// hardware does by itself; a hand-off that only works because of "natural" timing then hangs (the watchdog traps it)
+// or fails its parity check. tests/gpu_quick.py and the GPU suite are run against this build (tools/gpu_jitter.sh).
+#ifdef FA_JITTER
+FA_DEVICE void fa_jitter() {
+    uint32_t t;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(t));
+    t = (t ^ (t >> 7)) * 0x9E3779B1u + (threadIdx.x >> 5) * 0x85EBCA6Bu;
+    if ((t & 0x30000u) == 0u) {  // busy wait of up to ~8k clocks (a spin, not __nanosleep: the warp keeps its issue slot)
+        const uint32_t n = (t >> 19) & 0x1fffu;
+        uint32_t t0, t1;
+        asm volatile("mov.u32 %0, %%clock;" : "=r"(t0));
+        do {
+            asm volatile("mov.u32 %0, %%clock;" : "=r"(t1));
+        } while (t1 - t0 < n);
+    }
+}
+#else
+FA_DEVICE void fa_jitter() {}
+#endif
 FA_DEVICE void mbar_arrive(uint32_t bar) {
+#if defined(FA_JITTER) && (FA_JITTER + 0) != 1  // -DFA_JITTER=1: waits only, =2: arrivals only, otherwise both
+    fa_jitter();
+#endif
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 FA_DEVICE void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -60,7 +84,42 @@ FA_DEVICE bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // (profiles/experiments/README.md, round 2). Waits are bounded from the outside instead: one spare warp per CTA is
 // a watchdog (below) that traps the kernel when the CTA stops making progress.
 // -DFA_DEADLOCK_TRAP=<polls>: bring-up builds trap in place after a poll count (slow, but it names the barrier).
+// -DFA_WAIT_LOG: bring-up builds keep, per warp, the barrier (shared-memory address, parity) it is waiting on in a small
+// static shared array; when the watchdog fires it copies the 16 words of its CTA into a zero-copy pinned HOST buffer
+// handed in through fa_b200_debug_set_wait_log() -- the words survive the trap, and tools/wait_log.py prints where every
+// warp of a hung CTA sat. Word = 1 << 31 (still waiting) | parity << 30 | barrier address; host: [block][16 warps].
+#ifdef FA_WAIT_LOG
+__device__ unsigned long long* g_fa_wait_log = nullptr;
+FA_DEVICE volatile uint32_t* fa_wait_smem() {
+    __shared__ uint32_t words[16];
+    return words;
+}
+FA_DEVICE void fa_wait_log(uint32_t bar, uint32_t parity, uint32_t waiting) {
+    if ((threadIdx.x & 31) == 0) fa_wait_smem()[threadIdx.x >> 5] = (waiting << 31) | (parity << 30) | bar;
+}
+FA_DEVICE void fa_wait_log_dump() {  // called by the watchdog lane right before it traps
+    if (g_fa_wait_log && blockIdx.x < 256) {
+        for (int w = 0; w < 16; ++w) g_fa_wait_log[blockIdx.x * 16 + w] = 0x100000000ull | fa_wait_smem()[w];
+        __threadfence_system();
+    }
+}
+#else
+FA_DEVICE void fa_wait_log(uint32_t, uint32_t, uint32_t) {}
+FA_DEVICE void fa_wait_log_dump() {}
+#endif
 FA_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef FA_WAIT_LOG
+    fa_wait_log(bar, parity, 1);
+#endif
+#if defined(FA_JITTER) && (FA_JITTER + 0) != 2
+    fa_jitter();
+#endif
+#ifdef FA_WAIT_LOG
+    while (!mbar_try_wait(bar, parity)) {
+    }
+    fa_wait_log(bar, parity, 0);
+    return;
+#endif
 #ifdef FA_DEADLOCK_TRAP
     for (uint32_t polls = 0; !mbar_try_wait(bar, parity); ++polls) {
         if (polls > (uint32_t)(FA_DEADLOCK_TRAP)) __trap();
@@ -151,6 +210,7 @@ FA_DEVICE void watchdog_run(volatile uint32_t* wd, uint32_t bar_done, const vola
                     t_last = now;
                 } else if (now - t_last > (uint64_t)(FA_WATCHDOG_NS)) {
                     watchdog_report(wd, sdbg, report);
+                    fa_wait_log_dump();
                     __trap();
                 }
             }

@@ -46,7 +46,8 @@ def run_case(name, B, Sq, Sk, H, Hk, D, dtype, causal, window=(-1, -1), softcap=
             rec["ok"] = err < 2e-2
         # per-row-block error map to localise layout bugs
         e_rows = (out.double().cpu() - ref).abs().amax(dim=(0, 2, 3))
-        rec["err_by_rowblock"] = [round(x, 4) for x in e_rows.view(-1, min(64, Sq)).amax(dim=1).tolist()[:16]]
+        blk = min(64, Sq)
+        rec["err_by_rowblock"] = [round(x, 4) for x in e_rows[: Sq // blk * blk].view(-1, blk).amax(dim=1).tolist()[:16]]
     except Exception as ex:  # noqa: BLE001
         rec["error"] = f"{type(ex).__name__}: {ex}"
     print(json.dumps(rec), flush=True)

@@ -1,0 +1,8 @@
+#!/usr/bin/env bash
+# A/B: shared S buffer (default library) against -DFA_SHARED_S=0 (libfa_b200_sep.so); parity first.
+cd "$(dirname "$0")/.."
+out=gpurun_out/r02_18
+mkdir -p "$out"
+echo "=== parity (default lib)"; timeout 300 python tests/gpu_quick.py shared 2>&1 | grep -E '"ok": false|rror|"ms"' | cut -c1-160
+AB_FILTER="C2_bf16|S1024|_full|C2gqa|C5shard|S16384|D64|C3_" ROUNDS=2 FWD_KERNEL=1 bash tools/ab_v1.sh 2>&1 | tee "$out/ab_shared_s.log" | cut -c1-120
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 | tee "$out/tests.log"

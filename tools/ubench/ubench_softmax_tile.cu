@@ -1,0 +1,180 @@
+// How fast can one SM sub-partition run the forward's softmax when its warps never wait for S? (bring-up tool)
+// Each warp loops over "tiles": tcgen05.ld of 128 fp32 columns, row max (3-input max chains), lazy-rescale test,
+// exp2 (1/4 emulated on the FMA pipe), row sum, 16-bit pack, tcgen05.st of 64 columns -- the same statements as the
+// softmax warps of fwd_sm100.cuh, without any mbarrier. Reported: cycles per tile per warp and per scheduler, for
+// 1 / 2 / 3 / 4 warps per scheduler all running concurrently.
+//   nvcc -O3 -std=c++17 -arch=sm_100a -o ubench_softmax_tile ubench_softmax_tile.cu
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../flash-attention-v100_b200/csrc/ptx_sm100.cuh"
+#include "../../flash-attention-v100_b200/csrc/tmem_ldst_gen.cuh"
+using namespace fa;
+
+#ifndef MAXT
+#define MAXT 256  // 256 threads: up to 2 warps per scheduler with no register cap (the kernel gives its softmax warps 192)
+#endif
+#ifndef EMU_PERIOD
+#define EMU_PERIOD 4
+#endif
+#ifndef EMU_COUNT
+#define EMU_COUNT 1
+#endif
+
+template <int MODE>  // 0: full tile; 1: no max; 2: no TMEM traffic (registers only); 3: max computed but the exponentials
+                     // do not depend on it; 4: 2-input max tree; 5: max over packed halves (8 chains)
+__global__ void __launch_bounds__(MAXT, 1) k(float* out, const float* in, int iters, long long* cyc) {
+    __shared__ uint32_t tmem_ptr;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_ptr));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_ptr;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    // each warp of a scheduler gets its own 128 columns (4 warps per scheduler -> 512 columns)
+    const uint32_t tS = tmem_base + lane_off + (warp >> 2) * 128;
+    const uint32_t tP = tS + 64;
+    const float sl2 = in[1];
+    float m_ref = in[2];
+    float row_sum = 0.f;
+    {  // some finite data in TMEM
+        uint32_t z[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] = __float_as_uint(in[(lane * 32 + i) % 977]);
+        for (int c = 0; c < 4; ++c) tmem_st_x32(tS + c * 32, z);
+        tmem_wait_st();
+    }
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        float v[128];
+        if (MODE != 2) {
+            tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 128; ++i) v[i] = in[i] + (float)it;
+        }
+        float acc_scale = 1.0f;
+        float m_side = 0.f;
+        if (MODE == 4) {
+            float mx[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) mx[a] = fmaxf(v[2 * a], v[2 * a + 1]);
+#pragma unroll
+            for (int c = 16; c < 128; c += 16) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) mx[a] = fmaxf(mx[a], fmaxf(v[c + 2 * a], v[c + 2 * a + 1]));
+            }
+            const float m_new = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+            const float d = (m_ref - fmaxf(m_new, m_ref)) * sl2;
+            if (d < -8.0f) {
+                acc_scale = ex2_approx(d);
+                m_ref = m_new;
+            }
+        } else if (MODE == 5) {
+            float mx[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) mx[a] = fmaxf(v[2 * a], v[2 * a + 1]);
+#pragma unroll
+            for (int c = 16; c < 128; c += 16) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) mx[a] = fmax3(mx[a], v[c + 2 * a], v[c + 2 * a + 1]);
+            }
+            const float m_new = fmaxf(m_ref, fmax3(fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+            const float d = (m_ref - m_new) * sl2;
+            if (d < -8.0f) {
+                acc_scale = ex2_approx(d);
+                m_ref = m_new;
+            }
+        } else if (MODE != 1) {
+            float mx[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) mx[a] = fmaxf(v[2 * a], v[2 * a + 1]);
+#pragma unroll
+            for (int c = 8; c < 128; c += 8) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) mx[a] = fmax3(mx[a], v[c + 2 * a], v[c + 2 * a + 1]);
+            }
+            const float m_new = fmaxf(m_ref, fmax3(fmaxf(mx[0], mx[1]), mx[2], mx[3]));
+            const float d = (m_ref - m_new) * sl2;
+            if (MODE == 3) {
+                m_side = m_new;
+            } else if (d < -8.0f) {
+                acc_scale = ex2_approx(d);
+                m_ref = m_new;
+            }
+        }
+        const float neg_m = -m_ref * sl2;
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                float p0 = v[ch * 32 + c], p1 = v[ch * 32 + c + 1];
+                fma2(p0, p1, sl2, sl2, neg_m, neg_m);
+                if (EMU_COUNT > 0 && ((c / 2) % EMU_PERIOD) >= EMU_PERIOD - EMU_COUNT) {
+                    ex2_emu2(p0, p1);
+                } else {
+                    p0 = ex2_approx(p0);
+                    p1 = ex2_approx(p1);
+                }
+                add2(sum0, sum1, p0, p1);
+                pk[c / 2] = pack2<true>(p0, p1);
+            }
+            if (MODE != 2) {
+                tmem_st_x16(tP + ch * 16, pk);
+                if (ch >= 2) tmem_wait_st();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) row_sum += __uint_as_float(pk[i] & 0x3fffffffu);
+            }
+        }
+        row_sum = row_sum * acc_scale + (sum0 + sum1) + m_side;
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cyc[0] = t1 - t0;
+    out[threadIdx.x] = row_sum + m_ref;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+template <int MODE>
+void run(const char* name, float* out, float* in, long long* cyc) {
+    printf("%-40s", name);
+    for (int wps = 1; wps <= MAXT / 128; ++wps) {
+        const int iters = 200;
+        k<MODE><<<1, wps * 128>>>(out, in, iters, cyc);
+        cudaDeviceSynchronize();
+        k<MODE><<<1, wps * 128>>>(out, in, iters, cyc);
+        cudaDeviceSynchronize();
+        long long c;
+        cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("  w/s %d: %7.1f per warp-tile, %7.1f per tile per scheduler |", wps, (double)c / iters, (double)c / iters / wps);
+    }
+    printf("\n");
+}
+
+int main() {
+    float *out, *in;
+    long long* cyc;
+    cudaMalloc(&out, 4096 * 4);
+    cudaMalloc(&in, 4096 * 4);
+    cudaMalloc(&cyc, 8);
+    float h[4096];
+    for (int i = 0; i < 4096; ++i) h[i] = -0.01f * (i % 977);
+    h[1] = 0.127f;
+    h[2] = 0.5f;
+    cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
+    printf("emulated exponentials: %d of every %d pairs\n", EMU_COUNT, EMU_PERIOD);
+    run<0>("full tile (ld, max, exp, sum, pack, st)", out, in, cyc);
+    run<1>("no row max", out, in, cyc);
+    run<2>("registers only (no TMEM traffic)", out, in, cyc);
+    run<3>("max computed, exps independent of it", out, in, cyc);
+    run<4>("2-input max, 8 chains", out, in, cyc);
+    run<5>("3-input max, 8 chains", out, in, cyc);
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
