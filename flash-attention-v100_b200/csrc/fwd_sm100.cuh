@@ -191,7 +191,8 @@ struct FwdConfig {
     static constexpr int kOffRowMax = kOffRowSum + 2 * 2 * 128 * 4;  // [item parity][stage][128]
     static constexpr int kOffSched = kOffRowMax + 2 * 2 * 128 * 4;   // int[2] work ids (+ 8 bytes of padding)
     static constexpr int kOffClc = kOffSched + 16;                   // 16-byte cluster-launch-control response
-    static constexpr int kSmemUsed = kOffClc + 16;
+    static constexpr int kOffGeom = kOffClc + 16;                   // 2 x WorkHead (48 bytes each): the work mailbox's payload
+    static constexpr int kSmemUsed = kOffGeom + 2 * 48;
     static constexpr int kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
     // TMEM map. FA_SHARED_S = 0: S0 [0,128) S1 [128,256), P_s = upper half of S_s.
     // FA_SHARED_S = 1: ONE S buffer [0,128) that the stages use in turn (a softmax warp copies its S tile to registers
@@ -261,19 +262,43 @@ struct WorkGeom {
     bool skip;           // nothing to do and nothing to write (query block past the sequence end)
 };
 
-template <bool DECODE, bool SPLIT = false>
-FA_DEVICE WorkGeom work_geom(const FwdKernelParams& p, int work_id) {
-    constexpr int BM = 128, BN = 128;
-    constexpr int ROWS = SPLIT ? BM : 2 * BM;  // query rows per work item
-    WorkGeom w;
+// The expensive half of decoding a work id: the integer divisions of the launch order and the per-sequence loads.
+// 12 words; the loader publishes it through the work mailbox, the other roles finish it with shifts and min/max.
+struct alignas(16) WorkHead {
+    SeqGeom g;
+    int m_block, head, batch, kv_head, split, pad;
+};
+static_assert(sizeof(WorkHead) == 48, "WorkHead is copied as three 16-byte words");
+// field-by-field on purpose: taking the struct's address would put it in local memory
+FA_DEVICE void work_head_store(uint32_t smem, const WorkHead& h) {
+    st_shared_v4(smem, (uint32_t)h.g.q_off, (uint32_t)h.g.q_b, (uint32_t)h.g.seqlen_q, (uint32_t)h.g.k_off);
+    st_shared_v4(smem + 16, (uint32_t)h.g.k_b, (uint32_t)h.g.seqlen_k, (uint32_t)h.m_block, (uint32_t)h.head);
+    st_shared_v4(smem + 32, (uint32_t)h.batch, (uint32_t)h.kv_head, (uint32_t)h.split, 0u);
+}
+FA_DEVICE WorkHead work_head_load(uint32_t smem) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3;
+    ld_shared_v4(smem, a0, a1, a2, a3);
+    ld_shared_v4(smem + 16, b0, b1, b2, b3);
+    ld_shared_v4(smem + 32, c0, c1, c2, c3);
+    WorkHead h;
+    h.g.q_off = (int)a0; h.g.q_b = (int)a1; h.g.seqlen_q = (int)a2; h.g.k_off = (int)a3;
+    h.g.k_b = (int)b0; h.g.seqlen_k = (int)b1; h.m_block = (int)b2; h.head = (int)b3;
+    h.batch = (int)c0; h.kv_head = (int)c1; h.split = (int)c2; h.pad = 0;
+    return h;
+}
+
+template <bool DECODE>
+FA_DEVICE WorkHead work_head(const FwdKernelParams& p, int work_id) {
+    WorkHead h;
     const int G = DECODE ? p.gqa_pack : 1;
-    int m_block = 0;
-    w.split = 0;
+    h.m_block = 0;
+    h.split = 0;
+    h.pad = 0;
     if constexpr (DECODE) {
-        w.split = (int)blockIdx.x;
-        w.head = (int)blockIdx.y * G;  // first query head of the group
-        w.batch = blockIdx.z;
-        w.kv_head = blockIdx.y;
+        h.split = (int)blockIdx.x;
+        h.head = (int)blockIdx.y * G;  // first query head of the group
+        h.batch = blockIdx.z;
+        h.kv_head = blockIdx.y;
     } else {
         // sectioned longest-first order, see FwdKernelParams::section_bh
         const int per_section = p.section_bh * p.num_m_blocks;
@@ -282,12 +307,26 @@ FA_DEVICE WorkGeom work_geom(const FwdKernelParams& p, int work_id) {
         const int sec_n = min(p.section_bh, p.num_bh - sec * p.section_bh);
         const int m_rank = r / sec_n;
         const int bh = sec * p.section_bh + (r - m_rank * sec_n);
-        m_block = p.reverse_m ? p.num_m_blocks - 1 - m_rank : m_rank;
-        w.head = bh % p.num_heads;
-        w.batch = bh / p.num_heads;
-        w.kv_head = w.head / p.heads_per_kv;
+        h.m_block = p.reverse_m ? p.num_m_blocks - 1 - m_rank : m_rank;
+        h.head = bh % p.num_heads;
+        h.batch = bh / p.num_heads;
+        h.kv_head = h.head / p.heads_per_kv;
     }
-    w.g = load_geom(p, w.batch);
+    h.g = load_geom(p, h.batch);
+    return h;
+}
+
+template <bool DECODE, bool SPLIT = false>
+FA_DEVICE WorkGeom finish_geom(const FwdKernelParams& p, const WorkHead& h) {
+    constexpr int BM = 128, BN = 128;
+    constexpr int ROWS = SPLIT ? BM : 2 * BM;  // query rows per work item
+    WorkGeom w;
+    const int m_block = h.m_block;
+    w.split = h.split;
+    w.head = h.head;
+    w.batch = h.batch;
+    w.kv_head = h.kv_head;
+    w.g = h.g;
     w.m0 = m_block * ROWS;
     w.skip = w.m0 >= w.g.seqlen_q;  // over-provisioned varlen grid
     w.m_end = DECODE ? w.g.seqlen_q : min(w.m0 + ROWS, w.g.seqlen_q);
@@ -339,6 +378,11 @@ FA_DEVICE WorkGeom work_geom(const FwdKernelParams& p, int work_id) {
         if (w.n_tiles == 0) w.it_lo[s] = w.it_hi[s] = 0;
     }
     return w;
+}
+
+template <bool DECODE, bool SPLIT = false>
+FA_DEVICE WorkGeom work_geom(const FwdKernelParams& p, int work_id) {
+    return finish_geom<DECODE, SPLIT>(p, work_head<DECODE>(p, work_id));
 }
 
 // DECODE = false: persistent grid (one CTA per SM); work items = (256-row query block, head, batch) handed
@@ -447,16 +491,27 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
     }
 
     // Consumer side of the scheduler: k-th work id of this CTA (>= total_work means "no more work").
-    auto get_work = [&](int k) -> int {
+    // The loader decodes a work id ONCE (work_geom: a dozen integer divisions and, for var-len, dependent loads of the
+    // cu_seqlens entries -- ~2500 clocks in a 48-register warp, measured on the MMA warp between two items) and publishes
+    // the decoded geometry next to the id; every other role copies it out of shared memory.
+    const uint32_t sGeom = sbase + Cfg::kOffGeom;
+    struct Work {
+        int id;
+        WorkHead h;
+    };
+    auto get_work = [&](int k) -> Work {
+        Work r;
         if constexpr (DECODE) {
-            return k == 0 ? 0 : total_work;
+            r.id = k == 0 ? 0 : total_work;
+            r.h = work_head<DECODE>(p, 0);
         } else {
             mbar_wait(bar_sched_full(k & 1), (k >> 1) & 1);
-            const int id = sSched[k & 1];
+            r.id = sSched[k & 1];
+            r.h = work_head_load(sGeom + (k & 1) * 48);  // (garbage behind the end-of-work id: never used)
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_sched_empty(k & 1));
-            return id;
         }
+        return r;
     };
 
     if (warp == 13) {
@@ -495,13 +550,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
 #else
         // next unclaimed work id from this launch's counter (one atomic per CTA, broadcast to the warp)
         bool clc_more = !DECODE && p.sched != nullptr;
-        int pending_id = 0;
+        int pending_raw = 0;  // lane 0: the counter value on its way back (nothing waits for it until fetch_read)
         auto fetch_issue = [&]() {
-            int nid = 0;
-            if (lane == 0) nid = atomicAdd(p.sched, 1) + (int)gridDim.x;
-            pending_id = __shfl_sync(0xffffffffu, nid, 0);
+            if (lane == 0) pending_raw = atomicAdd(p.sched, 1) + (int)gridDim.x;
         };
         auto fetch_read = [&]() -> int {
+            const int pending_id = __shfl_sync(0xffffffffu, pending_raw, 0);
             if (pending_id >= total_work) clc_more = false;
             return pending_id < total_work ? pending_id : total_work;
         };
@@ -511,24 +565,33 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             fetch_issue();
             return fetch_read();
         };
+        WorkGeom w;
         for (int k = 0;; ++k) {
             if constexpr (!DECODE) {
                 // Query blocks past the end of their sequence (the var-len grid is sized for the longest
                 // sequence) have nothing to compute or write: drop them here instead of sending every warp
                 // through a scheduler hand-shake for them.
-                while (id < total_work && work_geom<DECODE, SPLIT>(p, id).skip) id = fetch();
-                // publish the k-th work id (slot k&1 is free once everyone consumed item k-2)
+                WorkHead h;
+                while (id < total_work) {
+                    h = work_head<DECODE>(p, id);
+                    w = finish_geom<DECODE, SPLIT>(p, h);
+                    if (!w.skip) break;
+                    id = fetch();
+                }
+                // publish the k-th work id and its geometry (slot k&1 is free once everyone consumed item k-2)
                 if (k >= 2) mbar_wait(bar_sched_empty(k & 1), ((k >> 1) - 1) & 1);
                 if (lane == 0) {
                     sSched[k & 1] = id;
+                    if (id < total_work) work_head_store(sGeom + (k & 1) * 48, h);
                     mbar_arrive(bar_sched_full(k & 1));
                 }
                 __syncwarp();
-            } else if (k > 0) {
-                id = total_work;
+            } else {
+                if (k > 0) id = total_work;
+                else w = work_geom<DECODE, SPLIT>(p, id);
             }
             if (id >= total_work) break;
-            const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
+            FA_TRACE_EV(303);  // loader: work id published
             const bool prefetching = clc_more;
             if (prefetching) fetch_issue();  // early: the request's latency hides behind the loads
             if (w.n_tiles > 0) {
@@ -547,6 +610,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     const int slot = ring % KV;
                     const uint32_t parity = ((ring / KV) & 1) ^ 1;
                     mbar_wait(bar_kv_empty(slot), parity);
+                    FA_TRACE_EV(310);  // loader: ring slot free
                     if (lane == 0) {
                         int row, b;
                         kv_coords(n, row, b);
@@ -554,14 +618,20 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     }
                     ++ring;
                 };
+                // The first K tile only needs a ring slot (free long before the previous item ends): it goes out first, so that
+                // at the item boundary only the Q tiles are still to come (an SM takes in ~40-60 B/clk: Q + K + V of a first
+                // iteration are 128 KB = ~2800 clocks after the Q buffer frees up, measured; Q alone is half of that).
+                produce(&p.tm_k, w.n_max - 1);
                 // Q tiles of the previous item must have been consumed by its last QK^T
+                FA_TRACE_EV(300);  // loader: waiting for the Q buffer
                 mbar_wait(bar_q_empty, (ka & 1) ^ 1);
+                FA_TRACE_EV(301);  // loader: Q buffer free
                 // DECODE: tm_q's box is (64, G, 128/G, 1), so one load brings the G heads of 128/G positions
                 if (lane == 0) load_tile(&p.tm_q, sQ, bar_q_full(0), w.head, w.g.q_off + w.m0, w.g.q_b);
-                produce(&p.tm_k, w.n_max - 1);
                 if (!DECODE && !SPLIT && lane == 0)
                     load_tile(&p.tm_q, sQ + Cfg::kTileBytes, bar_q_full(1), w.head, w.g.q_off + w.m0 + BM, w.g.q_b);
                 produce(&p.tm_v, w.n_max - 1);
+                FA_TRACE_EV(302);  // loader: Q0, K, Q1, V of the first iteration issued
                 for (int it = 1; it < w.n_tiles; ++it) {
                     produce(&p.tm_k, w.n_max - 1 - it);
                     produce(&p.tm_v, w.n_max - 1 - it);
@@ -615,21 +685,29 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         int steps[2] = {0, 0};  // softmax steps of earlier items, per stage (barrier phase bookkeeping)
         int sx_uses = 0;        // shared-S mode: Q K^T tiles written into the S buffer so far
         for (int k = 0;; ++k) {
-            const int id = get_work(k);
+            const Work wk = get_work(k);
+            const int id = wk.id;
             if (id >= total_work) break;
-            const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
+            const WorkGeom w = finish_geom<DECODE, SPLIT>(p, wk.h);
             if (w.n_tiles <= 0) continue;
+            // the item's last Q K^T in issue order (stage 1 is issued behind stage 0 within an iteration)
+            const int last0 = w.it_hi[0] > w.it_lo[0] ? w.it_hi[0] - 1 : -1, last1 = w.it_hi[1] > w.it_lo[1] ? w.it_hi[1] - 1 : -1;
+            const int last_qk_it = max(last0, last1);
+            const int last_qk_s = (last1 >= 0 && last1 == last_qk_it) ? 1 : 0;
+            FA_TRACE_EV(130);  // MMA: new item
             mbar_wait(bar_q_full(0), ka & 1);
+            FA_TRACE_EV(131);  // MMA: Q0 landed
             // Issue order per iteration. Separate S buffers: PV0(it-1) QK0(it) PV1(it-1) QK1(it) -- tcgen05 ops execute in
             // issue order, so S_s(it) may overwrite the columns P_s(it-1) lives in without a barrier. Shared S buffer:
             // QK0(it) PV0(it-1) QK1(it) PV1(it-1) -- a Q K^T only waits until the previous S tile (the other stage's, as a
             // rule) has been copied to registers, so it runs while its own stage is still busy with the tile before.
             // Either way the first QK^T of the next item may follow the last P V of this one directly.
             for (int it = 0; it <= w.n_tiles; ++it) {
-                if (it > 0) wait_full(ring + 2 * it - 1);
-                if (it == 1 && w.ragged_tail) mbar_wait(bar_vfix, kfix & 1);  // V rows past seqlen_k are zero now
                 if (it < w.n_tiles) wait_full(ring + 2 * it);
+                bool v_ready = false;  // V(it-1) is only waited for by the first P V of the iteration (a Q K^T does not need it)
                 if (!DECODE && !SPLIT && it == 0) mbar_wait(bar_q_full(1), ka & 1);
+                const bool qk0_this_it = it < w.n_tiles && it >= w.it_lo[0] && it < w.it_hi[0];
+                const bool qk1_this_it = it < w.n_tiles && it >= w.it_lo[1] && it < w.it_hi[1];
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     const bool do_pv = it > 0 && (it - 1) >= w.it_lo[s] && (it - 1) < w.it_hi[s];
@@ -643,10 +721,21 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         if (Cfg::kEarlyQK && do_pv) issue_qk_half(s, slot_addr(ring + 2 * it), 1);  // left half went ahead
                         else issue_qk(s, slot_addr(ring + 2 * it));
                         umma_commit_elect(bar_s_full(s));
+                        // the item's last Q K^T: the Q buffer is free as soon as it completes (a commit at the end of the
+                        // iteration would also wait for the P V issued behind it, i.e. for a whole softmax)
+                        if (it == last_qk_it && s == last_qk_s) umma_commit_elect(bar_q_empty);
+                        // likewise the K tile: free once the iteration's last Q K^T has read it (shared-S order only: there
+                        // a P V of the previous iteration is issued BEHIND this Q K^T and would hold the slot for a softmax)
+                        if (Cfg::kSharedS && (s == 1 || !qk1_this_it)) umma_commit_elect(bar_kv_empty((ring + 2 * it) % KV));
                         FA_TRACE_EV(120 + s);  // MMA: QK_s issued
                     };
                     if (Cfg::kSharedS && do_qk) qk();
                     if (do_pv) {
+                        if (!v_ready) {
+                            wait_full(ring + 2 * it - 1);
+                            if (it == 1 && w.ragged_tail) mbar_wait(bar_vfix, kfix & 1);  // V rows past seqlen_k are zero now
+                            v_ready = true;
+                        }
                         const int j = it - 1 - w.it_lo[s];
                         const uint32_t ph = (steps[s] + j) & 1;
                         const uint32_t tP = tPs[s];
@@ -681,8 +770,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     if (!Cfg::kSharedS && do_qk) qk();
                 }
                 if (it > 0) umma_commit_elect(bar_kv_empty((ring + 2 * it - 1) % KV));
-                if (it < w.n_tiles) umma_commit_elect(bar_kv_empty((ring + 2 * it) % KV));
-                if (it == w.n_tiles - 1) umma_commit_elect(bar_q_empty);  // last QK^T of the item issued
+                if (it < w.n_tiles && !(Cfg::kSharedS && (qk0_this_it || qk1_this_it))) umma_commit_elect(bar_kv_empty((ring + 2 * it) % KV));
+                // (bar_q_empty is committed right behind the item's last Q K^T, see qk(); an item none of whose stages has a
+                // tile -- possible with Sq > Sk and a window -- releases the Q buffer here)
+                if (last_qk_it < 0 && it == w.n_tiles - 1) umma_commit_elect(bar_q_empty);
             }
             ring += 2 * w.n_tiles;
             steps[0] += w.it_hi[0] - w.it_lo[0];
@@ -705,9 +796,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         int items = 0;  // earlier items in which this stage took part
 
         for (int k = 0;; ++k) {
-            const int id = get_work(k);
+            const Work wk = get_work(k);
+            const int id = wk.id;
             if (id >= total_work) break;
-            const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
+            const WorkGeom w = finish_geom<DECODE, SPLIT>(p, wk.h);
             const int my_lo = s == 0 ? w.it_lo[0] : w.it_lo[1];
             const int my_n = (s == 0 ? w.it_hi[0] : w.it_hi[1]) - my_lo;
             if (my_n <= 0) continue;
@@ -938,9 +1030,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         int items[2] = {0, 0};
 
         for (int k = 0;; ++k) {
-            const int id = get_work(k);
+            const Work wk = get_work(k);
+            const int id = wk.id;
             if (id >= total_work) break;
-            const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
+            const WorkGeom w = finish_geom<DECODE, SPLIT>(p, wk.h);
             if (w.skip) continue;
             if (w.n_tiles <= 0) {
                 // No visible key for any row of this block: out = 0, lse = sentinel (reference
@@ -1085,9 +1178,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         reg_dec<48>();
         int ring = 0;
         for (int k = 0;; ++k) {
-            const int id = get_work(k);
+            const Work wk = get_work(k);
+            const int id = wk.id;
             if (id >= total_work) break;
-            const WorkGeom w = work_geom<DECODE, SPLIT>(p, id);
+            const WorkGeom w = finish_geom<DECODE, SPLIT>(p, wk.h);
             if (w.n_tiles <= 0) continue;
             if (w.ragged_tail) {
                 const int v_entry = ring + 1;

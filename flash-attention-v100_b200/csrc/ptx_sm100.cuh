@@ -354,6 +354,9 @@ FA_DEVICE void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint3
                  "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
                  : "memory");
 }
+FA_DEVICE void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
 FA_DEVICE void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }

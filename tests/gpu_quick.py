@@ -79,7 +79,7 @@ def bench_case(name, B, S, H, Hk, D, dtype, causal, iters=10, window=(-1, -1)):
     results.append(rec)
 
 
-def bench_varlen(name, iters=20):
+def bench_varlen(name, iters=100):
     """BASELINE config 3: 64 packed sequences, randint(1, 2049) seed 0, H=32, D=128, bf16 causal."""
     from flash_attn_v100 import flash_attn_varlen_func
 
@@ -125,7 +125,7 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "default"
     if all(r.get("ok") for r in results):
         bench_case("C2_bf16_B8_H32_S4096_D128_causal", 8, 4096, 32, 32, 128, bf16, True, iters=30)
-        bench_case("bf16_B32_H32_S1024_D128_causal", 32, 1024, 32, 32, 128, bf16, True, iters=30)
+        bench_case("bf16_B32_H32_S1024_D128_causal", 32, 1024, 32, 32, 128, bf16, True, iters=200)
         bench_case("bf16_B8_H32_S4096_D128_full", 8, 4096, 32, 32, 128, bf16, False)
         bench_case("C2gqa_bf16_B8_H32_Hk8_S4096_causal", 8, 4096, 32, 8, 128, bf16, True, iters=20)
         bench_case("C5shard_bf16_B8_H32_S8192_win4096", 8, 8192, 32, 32, 128, bf16, True, window=(4096, 0))

@@ -30,7 +30,7 @@ NAMES = {6: "max done", 7: "prev PV done", 1: "S seen", 2: "S in regs", 3: "max+
          110: "mma P0 last", 111: "mma P1 last", 120: "mma QK0 issued", 121: "mma QK1 issued", 200: "corr stats0",
          201: "corr stats1", 210: "corr O0 final", 211: "corr O1 final", 220: "corr epi0 done", 221: "corr epi1 done", 230: "corr got id", 231: "corr geom", 400: "ask work", 401: "work slot full", 240: "corr last chunk0", 241: "corr last chunk1", 242: "corr tma read done0", 243: "corr tma read done1", 130: "mma new item", 131: "mma Q0 landed", 132: "mma K0,Q1 landed", 300: "load wait qempty", 301: "load q free", 302: "load first issued",
          102: "mma P2 seen", 122: "mma QK2 issued", 140: "mma K landed", 141: "mma V landed", 142: "mma PV issued",
-         310: "load slot free", 311: "load issued"}
+         310: "load slot free", 311: "load issued", 303: "load id published"}
 events = []
 for w in (0, 4, 8, 12, 13):
     for i in range(2048):
