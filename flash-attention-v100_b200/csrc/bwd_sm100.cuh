@@ -119,13 +119,6 @@ struct BwdConfig {
     static constexpr int kTmemT1 = 0, kTmemT2 = 128, kTmemOut1 = 256, kTmemOut2 = 256 + kOW;
 };
 
-FA_DEVICE void mul2(float& a0, float& a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\t"
-        "mul.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
-        : "+f"(a0), "+f"(a1)
-        : "f"(b0), "f"(b1));
-}
-
 FA_DEVICE uint32_t pack_half2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

@@ -791,7 +791,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tmem_base + lane_off + (s == 0 ? Cfg::kTmemS0 : Cfg::kTmemS1);
         const uint32_t tP = tmem_base + lane_off + (s == 0 ? Cfg::kTmemP0 : Cfg::kTmemP1);
-        const float sl2 = FEAT ? 1.0f : p.scale_log2;
+        // FEAT: S is transformed to log2 units in registers (sl2 = 1), except for soft-capping alone, where the registers
+        // keep tanh(score * scale / cap) and cap * log2(e) is folded into the exponent's FMA like the plain scale
+        const bool cap_only = FEAT && p.softcap > 0.f && p.alibi == nullptr;
+        const float sl2 = FEAT ? (cap_only ? p.softcap * kLog2e : 1.0f) : p.scale_log2;
         int steps = 0;  // softmax steps of earlier items (barrier phase bookkeeping)
         int items = 0;  // earlier items in which this stage took part
 
@@ -865,7 +868,17 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     const bool affine = p.softcap <= 0.f;
                     const bool all_left = affine && __all_sync(0xffffffffu, rel0 >= BN - 1);  // every column <= diagonal
                     const bool all_right = affine && __all_sync(0xffffffffu, rel0 <= 0);      // every column >= diagonal
-                    if (all_left || all_right) {
+                    if (cap_only) {
+                        // one packed multiply per pair and one MUFU.TANH per element (the general path below spends ~8
+                        // instructions per element on the same thing)
+                        const float c1 = p.scale * inv_cap;
+#pragma unroll
+                        for (int c = 0; c < BN; c += 2) {
+                            mul2(v[c], v[c + 1], c1, c1);
+                            v[c] = tanh_approx(v[c]);
+                            v[c + 1] = tanh_approx(v[c + 1]);
+                        }
+                    } else if (all_left || all_right) {
                         const float a = (all_left ? slope : -slope) * kLog2e;
                         const float b0 = -a * (float)rel0;
                         const float s2 = p.scale * kLog2e;

@@ -483,6 +483,12 @@ FA_DEVICE void fma2(float& a0, float& a1, float s0, float s1, float b0, float b1
         : "+f"(a0), "+f"(a1)
         : "f"(s0), "f"(s1), "f"(b0), "f"(b1));
 }
+FA_DEVICE void mul2(float& a0, float& a1, float s0, float s1) {
+    asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\t"
+        "mul.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(s0), "f"(s1));
+}
 FA_DEVICE void add2(float& a0, float& a1, float b0, float b1) {
     asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\t"
         "add.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
