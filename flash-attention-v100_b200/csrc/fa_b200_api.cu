@@ -803,11 +803,11 @@ FA_B200_API int fa_b200_kvcache_fwd(const fa_b200_params_t* p, void* stream_v) {
         rp.interleaved = p->rotary_interleaved;
         rp.per_row_pos = (causal || wl >= 0 || wr >= 0) ? 1 : 0;
         const int64_t total = (int64_t)p->batch * p->seqlen_q * p->num_heads * (p->head_dim / 8);
-        if (total > prep_total) prep_total = total;
-        const int blocks = (int)((prep_total + 255) / 256 < 148 * 8 ? (prep_total + 255) / 256 : 148 * 8);
-        // rotary implies has_new (checked above): append + RoPE(K) + RoPE(Q) in one launch
-        if (bf16) fa::kv_prep_kernel<true><<<blocks, 256, 0, stream>>>(ap, rp);
-        else fa::kv_prep_kernel<false><<<blocks, 256, 0, stream>>>(ap, rp);
+        auto blocks_for = [](int64_t n) { return (int)((n + 127) / 128 < 148 * 4 ? (n + 127) / 128 : 148 * 4); };
+        const int append_blocks = blocks_for(prep_total), q_blocks = blocks_for(total);
+        // rotary implies has_new (checked above): append + RoPE(K) + RoPE(Q) in one launch, on disjoint CTAs
+        if (bf16) fa::kv_prep_kernel<true><<<append_blocks + q_blocks, 128, 0, stream>>>(ap, rp, append_blocks);
+        else fa::kv_prep_kernel<false><<<append_blocks + q_blocks, 128, 0, stream>>>(ap, rp, append_blocks);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "kv_prep_kernel launch");

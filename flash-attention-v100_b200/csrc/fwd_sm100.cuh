@@ -834,9 +834,33 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                              (int64_t)(w.g.q_off + i_glob) * p.dmask_stride_row;
             }
 
+            // DECODE packs (position, head-in-group) pairs into the tile's rows: with one new token and a group of 4 only rows
+            // 0..3 are real. A warp all of whose 32 rows are padding keeps every hand-shake but skips the arithmetic, which
+            // leaves the sub-partitions to the one warp that has rows (its softmax is the decode chain's longest link).
+            // P and O of padded rows are never stored, and the MMA keeps rows independent.
+            const bool lazy_warp = DECODE && (warp & 3) * 32 >= G * w.g.seqlen_q;
+            if (lazy_warp) {  // "no rescale" for both tile parities (the correction warps read sScale of every row)
+                sScale[(0 * 2 + s) * BM + row] = 1.0f;
+                sScale[(1 * 2 + s) * BM + row] = 1.0f;
+                __syncwarp();
+            }
+
             for (int j = 0; j < my_n; ++j) {
                 const int j0 = (w.n_max - 1 - (my_lo + j)) * BN;
                 mbar_wait(bar_s_full(s), (steps + j) & 1);
+                if (lazy_warp) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (Cfg::kEarlyQK || Cfg::kSharedS) mbar_arrive(Cfg::kSharedS ? bar_sx_free : bar_s_loaded(s));
+                        mbar_arrive(bar_stats(s, (steps + j) & 1));  // (sScale of padded rows is never looked at: see below)
+                    }
+                    if (Cfg::kSharedS && steps + j > 0) mbar_wait(bar_p_free(s), (steps + j - 1) & 1);
+                    if (lane == 0) {
+                        mbar_arrive(bar_p_full(s));
+                        if (FA_SPLIT_P) mbar_arrive(bar_p_last(s));
+                    }
+                    continue;
+                }
                 tc_fence_after();
                 FA_TRACE_EV(1);  // softmax: S observed
                 float v[BN];
@@ -1226,6 +1250,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
 
 // Merge the split-KV partials of the decode path: out = sum_i w_i O_i / sum_i w_i with
 // w_i = exp(lse_i - max lse), lse = max + ln(sum w_i). One warp per (batch, head, position) row.
+// Latency, not bandwidth, is what this kernel costs (a B=1 decode step has 32 rows): lane i fetches the LSE of
+// split i (and i + 32), so all of them are in flight at once, the max and the weight sum are warp reductions, and the
+// partial rows are fetched four splits at a time before any of them is used.
 template <int D, bool BF16>
 __global__ void fa_combine_kernel(const float* __restrict__ o_partial, const float* __restrict__ lse_partial,
                                   uint16_t* __restrict__ out, float* __restrict__ lse, int num_splits, int batch,
@@ -1237,22 +1264,51 @@ __global__ void fa_combine_kernel(const float* __restrict__ o_partial, const flo
     pdl_wait_primary();  // launched with programmatic stream serialisation behind the decode kernel
     if (row >= rows) return;
     const int pos = row % seqlen_q, h = (row / seqlen_q) % heads, b = row / ((int64_t)seqlen_q * heads);
-    float mx = -INFINITY;
-    for (int i = 0; i < num_splits; ++i) mx = fmaxf(mx, lse_partial[(int64_t)i * rows + row]);
+    // num_splits <= 64 (decode_num_splits)
+    const float l0 = lane < num_splits ? lse_partial[(int64_t)lane * rows + row] : -INFINITY;
+    const float l1 = lane + 32 < num_splits ? lse_partial[(int64_t)(lane + 32) * rows + row] : -INFINITY;
+    float mx = fmaxf(l0, l1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float w0 = (mx > -INFINITY && l0 > -INFINITY) ? __expf(l0 - mx) : 0.f;
+    const float w1 = (mx > -INFINITY && l1 > -INFINITY) ? __expf(l1 - mx) : 0.f;
+    float wsum = w0 + w1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
     constexpr int E = D / 32;  // elements per lane
     float acc[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) acc[e] = 0.f;
-    float wsum = 0.f;
-    if (mx > -INFINITY) {
-        for (int i = 0; i < num_splits; ++i) {
-            const float w = __expf(lse_partial[(int64_t)i * rows + row] - mx);
-            if (w > 0.f) {
-                const float* src = o_partial + ((int64_t)i * rows + row) * D + lane * E;
+    const float* src0 = o_partial + row * D + lane * E;
+    for (int i0 = 0; i0 < num_splits; i0 += 4) {
+        float part[4][E];
+        float wi[4];
 #pragma unroll
-                for (int e = 0; e < E; ++e) acc[e] += w * src[e];
-                wsum += w;
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u;
+            const float wa = __shfl_sync(0xffffffffu, w0, i & 31), wb = __shfl_sync(0xffffffffu, w1, i & 31);
+            wi[u] = i < num_splits ? (i < 32 ? wa : wb) : 0.f;
+            if (wi[u] > 0.f) {
+                const float* src = src0 + (int64_t)i * rows * D;
+                if constexpr (E >= 4) {
+#pragma unroll
+                    for (int e = 0; e < E; e += 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(src + e);
+                        part[u][e] = t.x; part[u][e + 1] = t.y; part[u][e + 2] = t.z; part[u][e + 3] = t.w;
+                    }
+                } else {
+                    const float2 t = *reinterpret_cast<const float2*>(src);
+                    part[u][0] = t.x; part[u][1] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) part[u][e] = 0.f;
             }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = fmaf(wi[u], part[u][e], acc[e]);
         }
     }
     const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;

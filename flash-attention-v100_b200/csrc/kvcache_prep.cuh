@@ -87,11 +87,11 @@ __device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontro
 
 // one thread per 8 consecutive elements of one (batch, new row, kv head)
 template <bool BF16>
-__device__ __forceinline__ void kv_append_body(const AppendParams& p) {
+__device__ __forceinline__ void kv_append_body(const AppendParams& p, int block, int num_blocks) {
     const int chunks = p.head_dim / 8;
     const int64_t total = (int64_t)p.batch * p.seqlen_new * p.heads_k * chunks;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t idx = block * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)num_blocks * blockDim.x) {
         const int chunk = idx % chunks;
         const int hk = (idx / chunks) % p.heads_k;
         const int r = (idx / ((int64_t)chunks * p.heads_k)) % p.seqlen_new;
@@ -142,11 +142,11 @@ struct QRotaryParams {
 };
 
 template <bool BF16>
-__device__ __forceinline__ void q_rotary_body(const QRotaryParams& p) {
+__device__ __forceinline__ void q_rotary_body(const QRotaryParams& p, int block, int num_blocks) {
     const int chunks = p.head_dim / 8;
     const int64_t total = (int64_t)p.batch * p.seqlen_q * p.heads * chunks;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t idx = block * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)num_blocks * blockDim.x) {
         const int chunk = idx % chunks;
         const int h = (idx / chunks) % p.heads;
         const int r = (idx / ((int64_t)chunks * p.heads)) % p.seqlen_q;
@@ -174,20 +174,21 @@ __device__ __forceinline__ void q_rotary_body(const QRotaryParams& p) {
 template <bool BF16>
 __global__ void kv_append_kernel(const AppendParams p) {
     pdl_launch_dependents();
-    kv_append_body<BF16>(p);
+    kv_append_body<BF16>(p, (int)blockIdx.x, (int)gridDim.x);
 }
 template <bool BF16>
 __global__ void q_rotary_kernel(const QRotaryParams p) {
     pdl_launch_dependents();
-    q_rotary_body<BF16>(p);
+    q_rotary_body<BF16>(p, (int)blockIdx.x, (int)gridDim.x);
 }
 // append + RoPE(K) and RoPE(Q) in ONE launch (a decode step needs both; each launch costs the host ~2.5 us and the
-// GPU a dependent-launch gap)
+// GPU a dependent-launch gap). The first `append_blocks` CTAs append, the others rotate Q: both jobs are chains of
+// dependent loads (cache_seqlens -> block table -> rows and angles), so they run side by side, not one after the other.
 template <bool BF16>
-__global__ void kv_prep_kernel(const AppendParams ap, const QRotaryParams rp) {
+__global__ void kv_prep_kernel(const AppendParams ap, const QRotaryParams rp, int append_blocks) {
     pdl_launch_dependents();
-    kv_append_body<BF16>(ap);
-    q_rotary_body<BF16>(rp);
+    if ((int)blockIdx.x < append_blocks) kv_append_body<BF16>(ap, (int)blockIdx.x, append_blocks);
+    else q_rotary_body<BF16>(rp, (int)blockIdx.x - append_blocks, (int)gridDim.x - append_blocks);
 }
 
 }  // namespace fa
