@@ -338,6 +338,14 @@ bool decode_applies(const fa_b200_params_t* p) {
 // KV splits per (batch, kv head): fill the 148 SMs for several waves but keep >= 4 tiles per split.
 int decode_num_splits(const fa_b200_params_t* p) {
     if (p->num_splits == 1) return 1;
+    static const int forced = [] {  // tuning aid (tools/gpu_call_r02_23.sh): FA_B200_DECODE_SPLITS=<n> overrides the heuristic
+        const char* e = getenv("FA_B200_DECODE_SPLITS");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced > 0) {
+        const int tiles_f = (p->seqlen_k + 127) / 128;
+        return forced < tiles_f ? (forced < 64 ? forced : 64) : (tiles_f < 64 ? tiles_f : 64);
+    }
     const int tiles = (p->seqlen_k + 127) / 128;
     const int64_t base = (int64_t)p->batch * p->num_heads_k;
     int best = 1;
