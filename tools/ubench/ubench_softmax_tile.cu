@@ -21,11 +21,19 @@ using namespace fa;
 #define EMU_COUNT 1
 #endif
 
-template <int MODE>  // 0: full tile; 1: no max; 2: no TMEM traffic (registers only); 3: max computed but the exponentials
+template <int MODE, int OVH = 0>  // OVH (mode 0 only): bit 0 four syncwarp + elected mbarrier arrivals per tile, bit 1 three waits on
+                              // completed mbarriers, bit 2 tcgen05 fences, bit 3 stats store, bit 4 mask vote.  MODE 0: full tile; 1: no max; 2: no TMEM traffic (registers only); 3: max computed but the exponentials
                      // do not depend on it; 4: 2-input max tree; 5: max over packed halves (8 chains)
 __global__ void __launch_bounds__(MAXT, 1) k(float* out, const float* in, int iters, long long* cyc) {
     __shared__ uint32_t tmem_ptr;
+    __shared__ uint64_t bars[4];
+    __shared__ float s_scale[512];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bars[0]), 1000000u);  // arrive target: never completes
+        mbar_init(smem_u32(&bars[1]), 1);         // wait target: completed once below, waited for with the old parity
+        mbar_fence_init();
+    }
     if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_ptr));
     tc_fence_before();
     __syncthreads();
@@ -46,11 +54,29 @@ __global__ void __launch_bounds__(MAXT, 1) k(float* out, const float* in, int it
         tmem_wait_st();
     }
     __syncthreads();
+    if (threadIdx.x == 0) mbar_arrive(smem_u32(&bars[1]));
+    __syncthreads();
+    const uint32_t bar_a = smem_u32(&bars[0]), bar_w = smem_u32(&bars[1]);
+    auto arrive = [&]() {
+        if (OVH & 4) tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a);
+    };
+    auto wait_done = [&]() {
+        mbar_wait(bar_w, 0);
+        if (OVH & 4) tc_fence_after();
+    };
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
         float v[128];
+        if (OVH & 2) wait_done();  // s_full
+        if (OVH & 16) {
+            const bool need = (it & 1023) == 1023 && lane == 5;
+            if (__any_sync(0xffffffffu, need)) row_sum += 1.0f;
+        }
         if (MODE != 2) {
             tmem_ld_4x32_wait(tS, reinterpret_cast<uint32_t*>(v));
+            if (OVH & 1) arrive();  // sx_free
         } else {
 #pragma unroll
             for (int i = 0; i < 128; ++i) v[i] = in[i] + (float)it;
@@ -105,6 +131,8 @@ __global__ void __launch_bounds__(MAXT, 1) k(float* out, const float* in, int it
                 m_ref = m_new;
             }
         }
+        if (OVH & 8) s_scale[threadIdx.x & 511] = acc_scale;
+        if (OVH & 1) arrive();  // stats
         const float neg_m = -m_ref * sl2;
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
@@ -124,8 +152,12 @@ __global__ void __launch_bounds__(MAXT, 1) k(float* out, const float* in, int it
                 pk[c / 2] = pack2<true>(p0, p1);
             }
             if (MODE != 2) {
+                if (ch == 0 && (OVH & 2)) wait_done();  // p_free
                 tmem_st_x16(tP + ch * 16, pk);
-                if (ch >= 2) tmem_wait_st();
+                if (ch >= 2) {
+                    tmem_wait_st();
+                    if (OVH & 1) arrive();  // p_full (3/4), p_last
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) row_sum += __uint_as_float(pk[i] & 0x3fffffffu);
@@ -141,14 +173,14 @@ __global__ void __launch_bounds__(MAXT, 1) k(float* out, const float* in, int it
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
-template <int MODE>
+template <int MODE, int OVH = 0>
 void run(const char* name, float* out, float* in, long long* cyc) {
     printf("%-40s", name);
     for (int wps = 1; wps <= MAXT / 128; ++wps) {
         const int iters = 200;
-        k<MODE><<<1, wps * 128>>>(out, in, iters, cyc);
+        k<MODE, OVH><<<1, wps * 128>>>(out, in, iters, cyc);
         cudaDeviceSynchronize();
-        k<MODE><<<1, wps * 128>>>(out, in, iters, cyc);
+        k<MODE, OVH><<<1, wps * 128>>>(out, in, iters, cyc);
         cudaDeviceSynchronize();
         long long c;
         cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
@@ -172,6 +204,12 @@ int main() {
     run<0>("full tile (ld, max, exp, sum, pack, st)", out, in, cyc);
     run<1>("no row max", out, in, cyc);
     run<2>("registers only (no TMEM traffic)", out, in, cyc);
+    run<0, 1>("full tile + 4 arrivals", out, in, cyc);
+    run<0, 2>("full tile + 2 waits on done barriers", out, in, cyc);
+    run<0, 3>("full tile + arrivals + waits", out, in, cyc);
+    run<0, 7>("full tile + arrivals + waits + tc fences", out, in, cyc);
+    run<0, 15>("... + stats store", out, in, cyc);
+    run<0, 31>("... + mask vote (all kernel hand-shakes)", out, in, cyc);
     run<3>("max computed, exps independent of it", out, in, cyc);
     run<4>("2-input max, 8 chains", out, in, cyc);
     run<5>("3-input max, 8 chains", out, in, cyc);
