@@ -28,3 +28,5 @@ cat "$out/sass_mnemonics.txt"
 tail -2 "$out/varlen_c3.log" | cut -c1-200; tail -6 "$out/features.log" | cut -c1-200; tail -6 "$out/decode_c4.log" | cut -c1-220
 tail -6 "$out/host_overhead.log" | cut -c1-200; tail -7 "$out/bwd_quick.log" | cut -c1-200; head -12 "$out/ncu_fwd_c2.summary.txt"
 du -sh "$out"
+# the opt-in forward v2 (three S buffers, 128-row CTAs / CTA pairs) must still be parity-clean
+for m in 2s 2p; do echo "== FA_B200_FWD_KERNEL=$m"; FA_B200_FWD_KERNEL=$m QUICK_PARITY_ONLY=1 timeout 200 python tests/gpu_quick.py v$m 2>&1 | grep -E '"ok": false|rror|elapsed' | cut -c1-160; done | tee "$out/fwd_v2_parity.log"
