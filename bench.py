@@ -632,7 +632,9 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
         except Exception as e:  # noqa: BLE001  (an extra yardstick must never cost the bench line)
             cpu_baseline["torch_sdpa"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    tpath = os.path.join(ROOT, "profiles", "r02", "traffic_r02.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload)
     line = {
