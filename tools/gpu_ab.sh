@@ -9,7 +9,7 @@ L=$PWD/flash-attention-v100_b200/lib
 echo "=== parity (default lib)"; timeout 300 python tests/gpu_quick.py parity 2>&1 | grep -E '"ok": false|rror' | cut -c1-200
 for round in $(seq 1 ${ROUNDS:-2}); do
 for lib in $L/libfa_b200*.so; do
-  case "$lib" in *trace*) continue;; esac
+  case "$lib" in *trace*|*jitter*) continue;; esac
   tag=$(basename "$lib" .so); tag=${tag#libfa_b200}; tag=${tag#_}; tag=${tag:-default}
   echo "=== $tag (round $round)"
   QUICK_BENCH_ONLY=1 FA_B200_LIB="$lib" timeout -s KILL ${AB_TIMEOUT:-90} python tests/gpu_quick.py "$tag" 2>&1 | grep -E '"ms"|rror|Traceback' | grep -E "${AB_FILTER:-C2_bf16|S1024|_full|C2gqa|S16384|D64|C3_}" | sed -E 's/"ms": ([0-9.]{6})[0-9]*, "tflops": ([0-9.]{6})[0-9]*/\1 ms \2 TF/' | cut -c1-100
