@@ -341,6 +341,37 @@ def bench_c3(dev):
                                                  "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peak}}
 
 
+def bench_widened(dev):
+    """SURVEY 8(f) rows at the config-2 shape, for the driver record: the same shape non-causal, the backward (dense,
+    through autograd: row-dot + dK/dV pass + dQ pass; 10 D FLOP per unmasked pair = 2.5 x the forward), and the
+    score-modifier variants of the forward. bf16 B=8 H=32 S=4096 D=128."""
+    import torch
+    from flash_attn_v100 import flash_attn_func
+
+    B, S, H, D = 8, 4096, 32, 128
+    torch.manual_seed(421)
+    q, k, v = (torch.randn(B, S, H, D, device=dev, dtype=torch.bfloat16, requires_grad=True) for _ in range(3))
+    do = torch.randn(B, S, H, D, device=dev, dtype=torch.bfloat16)
+    slopes = (torch.rand(H, device=dev) * 0.2).float()
+    peak, _, _ = measured_peaks()
+    fl = 4.0 * D * B * H * S * S
+
+    def rec(ms, flops, bound="tensor"):
+        return {"value": flops / ms / 1e9, "unit": UNIT, "ms": ms, "roofline": {"bound": bound, "frac": flops / ms / 1e9 / peak, "peak": peak}}
+
+    out = {}
+    with torch.no_grad():
+        out["fwd_noncausal"] = rec(_time_events(lambda i: flash_attn_func(q, k, v), 10), fl)
+        out["fwd_alibi"] = rec(_time_events(lambda i: flash_attn_func(q, k, v, causal=True, alibi_slopes=slopes), 10), fl / 2)
+        out["fwd_softcap30"] = rec(_time_events(lambda i: flash_attn_func(q, k, v, causal=True, softcap=30.0), 10), fl / 2)
+        out["fwd_window1024"] = rec(_time_events(lambda i: flash_attn_func(q, k, v, causal=True, window_size=(1024, 0)), 10),
+                                    4.0 * D * B * H * (1024 * 1025 // 2 + (S - 1024) * 1025))
+        out["fwd_dropout0.1"] = rec(_time_events(lambda i: flash_attn_func(q, k, v, causal=True, dropout_p=0.1), 5), fl / 2)
+    o = flash_attn_func(q, k, v, causal=True)
+    out["bwd_causal"] = rec(_time_events(lambda i: torch.autograd.grad(o, (q, k, v), do, retain_graph=True), 10), 2.5 * fl / 2)
+    return {"workload": "config-2 shape (bf16 B=8 H=32 S=4096 D=128): non-causal forward, feature variants, backward", **out}
+
+
 def bench_c4(dev, B, Hk=8):
     """BASELINE config 4: flash_attn_with_kvcache bf16 decode, q_seqlen 1, kv_seqlen 8192, 32 heads, D=128, rotary,
     paged block_table (page 256). HBM-bound: achieved GB/s = attended K+V bytes / time. The step is the
@@ -603,6 +634,7 @@ def run_ours(args, w, rank: int, world: int, local_rank: int):
         if rank == 0:
             guarded("C1", lambda: bench_c1(dev))
             guarded("C3", lambda: bench_c3(dev))
+            guarded("widened", lambda: bench_widened(dev))
             for Bd in (1, 8, 64):
                 guarded(f"C4_B{Bd}", lambda: bench_c4(dev, Bd))
             torch.cuda.empty_cache()
