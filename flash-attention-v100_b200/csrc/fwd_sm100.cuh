@@ -9,17 +9,23 @@
 // include/gemm_smem.h:119-205). Only the semantics are shared; the schedule is Blackwell-native:
 //
 //   * one CTA = 2 query tiles of 128 rows ("stages") x one (batch, head); KV streamed in 128-row tiles
-//   * warp 13 : TMA producer  (Q once, then K/V tiles into a ring of 128B-swizzled smem slots)
-//   * warp 12 : tcgen05.mma issuer.  S_s = Q_s K^T (SS form), O_s += P_s V (TS form, P read from
-//               TMEM, V consumed as the MN-major B operand).  Accumulators never leave TMEM.
-//   * warps 0-3 / 4-7 : softmax for stage 0 / 1.  thread == row (tcgen05.ld 32x32b), so the row
-//               max / row sum are thread-local; P is written back over S in TMEM as 16-bit pairs.
+//   * warp 13 : TMA producer + tile scheduler (decodes each work id once and publishes id + geometry through a
+//               shared-memory mailbox; first K tile, Q, then K/V tiles into a ring of 128B-swizzled smem slots)
+//   * warp 12 : tcgen05.mma issuer.  S = Q_s K^T (SS form) into the ONE S buffer the stages share, O_s += P_s V (TS
+//               form, P read from TMEM, V consumed as the MN-major B operand).  Accumulators never leave TMEM.
+//               Issue order per iteration: QK0(it) PV0(it-1) QK1(it) PV1(it-1).
+//   * warps 0-3 / 4-7 : softmax for stage 0 / 1.  thread == row (tcgen05.ld 32x32b), so the row max / row sum are
+//               thread-local; S is copied to registers (which frees the S buffer for the other stage's next
+//               Q K^T), P is written to the stage's own P buffer in TMEM as 16-bit pairs.
 //   * warps 8-11 : correction (lazy rescale of O in TMEM when the running max moved by > 2^8)
 //               and the epilogue (O / l -> 16-bit -> global, LSE).
+//   * warp 14 : zeroes the rows of a ragged V tile past seqlen_k;  warp 15 : watchdog.
 //   * everything is ordered with mbarriers; tcgen05.commit signals MMA completion.
 //
-// TMEM map (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D);
-// P_s aliases columns [64,128) of S_s (128 x 128 16-bit values = 64 columns).
+// TMEM map (512 columns), FA_SHARED_S = 1 (default):  S [0,128)  P0 [128,192)  P1 [192,256)  O0 [256,256+D)
+// O1 [256+D,256+2D).  A softmax warp has its S tile in registers ~200 clocks after it lands, so one S buffer serves
+// both stages in turn and Q K^T(j+1) of a stage never waits for that stage's softmax(j) -> P V(j) (see FwdConfig).
+// FA_SHARED_S = 0 (round 1, kept for A/B): S0 [0,128) S1 [128,256), P_s aliases columns [64,128) of S_s.
 //
 // head_dim 256 ("split-D"): an O accumulator of 256 columns per query tile leaves no room for two stages, so
 // the two stages work on the SAME 128 query rows and each owns one 128-column half of O (stage s multiplies P
