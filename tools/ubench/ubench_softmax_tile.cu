@@ -9,10 +9,11 @@
 #include <cuda_runtime.h>
 #include "../../flash-attention-v100_b200/csrc/ptx_sm100.cuh"
 #include "../../flash-attention-v100_b200/csrc/tmem_ldst_gen.cuh"
+#include "../../flash-attention-v100_b200/csrc/umma_issue_gen.cuh"
 using namespace fa;
 
 #ifndef MAXT
-#define MAXT 256  // 256 threads: up to 2 warps per scheduler with no register cap (the kernel gives its softmax warps 192)
+#define MAXT 288  // 256 threads: up to 2 warps per scheduler with no register cap (the kernel gives its softmax warps 192)
 #endif
 #ifndef EMU_PERIOD
 #define EMU_PERIOD 4
@@ -21,10 +22,12 @@ using namespace fa;
 #define EMU_COUNT 1
 #endif
 
-template <int MODE, int OVH = 0>  // OVH (mode 0 only): bit 0 four syncwarp + elected mbarrier arrivals per tile, bit 1 three waits on
+template <int MODE, int OVH = 0, int MMA = 0>  // MMA = 1: an extra warp keeps the tensor pipe busy with the forward's two GEMMs
+                              // (S = Q K^T SS-form from shared memory, O += P V TS-form with P read from TMEM) on dummy data. OVH (mode 0 only): bit 0 four syncwarp + elected mbarrier arrivals per tile, bit 1 three waits on
                               // completed mbarriers, bit 2 tcgen05 fences, bit 3 stats store, bit 4 mask vote.  MODE 0: full tile; 1: no max; 2: no TMEM traffic (registers only); 3: max computed but the exponentials
                      // do not depend on it; 4: 2-input max tree; 5: max over packed halves (8 chains)
 __global__ void __launch_bounds__(MAXT, 1) k(float* out, const float* in, int iters, long long* cyc) {
+    extern __shared__ uint8_t dyn_smem[];
     __shared__ uint32_t tmem_ptr;
     __shared__ uint64_t bars[4];
     __shared__ float s_scale[512];
@@ -32,6 +35,8 @@ __global__ void __launch_bounds__(MAXT, 1) k(float* out, const float* in, int it
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&bars[0]), 1000000u);  // arrive target: never completes
         mbar_init(smem_u32(&bars[1]), 1);         // wait target: completed once below, waited for with the old parity
+        mbar_init(smem_u32(&bars[2]), 1);         // MMA hog: commit barrier
+        bars[3] = 0;                              // MMA hog: stop flag
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_ptr));
@@ -66,6 +71,30 @@ __global__ void __launch_bounds__(MAXT, 1) k(float* out, const float* in, int it
         mbar_wait(bar_w, 0);
         if (OVH & 4) tc_fence_after();
     };
+    if (MMA && warp == (int)(blockDim.x >> 5) - 1) {
+        // tensor-pipe hog: per "iteration" two tiles' worth of GEMMs (2 x (QK^T + PV) = 2048 tensor clocks), paced by a
+        // commit barrier so that the issue queue never runs dry nor overflows; stops when the softmax warps are done
+        const uint32_t sb = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t q_lo = ((sb & 0x3FFFFu) >> 4) | (1u << 16), k_lo = (((sb + 32768) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t v_lo = (((sb + 65536) & 0x3FFFFu) >> 4) | ((uint32_t)(16384 >> 4) << 16);
+        constexpr uint32_t idesc_qk = umma_idesc_f16(true, 128, 128, false, false), idesc_pv = umma_idesc_f16(true, 128, 128, false, true);
+        const uint32_t bar_m = smem_u32(&bars[2]);
+        volatile int* stop = reinterpret_cast<volatile int*>(&bars[3]);
+        int n = 0;
+        while (*stop == 0) {
+            tc_fence_after();
+            umma_issue_qk_d128(tmem_base + 256, q_lo, k_lo, kDescHi, kDescHi, idesc_qk);
+            umma_issue_pv_k0_8(tmem_base + 384, tmem_base + 64, v_lo, 0, kDescHi, idesc_pv, 1u);
+            umma_issue_qk_d128(tmem_base + 256, q_lo, k_lo, kDescHi, kDescHi, idesc_qk);
+            umma_issue_pv_k0_8(tmem_base + 384, tmem_base + 192, v_lo, 0, kDescHi, idesc_pv, 1u);
+            umma_commit_elect(bar_m);
+            if (n >= 1) mbar_wait(bar_m, (n - 1) & 1);  // at most two iterations in flight
+            ++n;
+        }
+        mbar_wait(bar_m, (n - 1) & 1);
+        if (lane == 0) cyc[1] = n;
+    } else {
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
         float v[128];
@@ -168,22 +197,30 @@ __global__ void __launch_bounds__(MAXT, 1) k(float* out, const float* in, int it
     const long long t1 = clock64();
     if (threadIdx.x == 0) cyc[0] = t1 - t0;
     out[threadIdx.x] = row_sum + m_ref;
+    if (MMA) {
+        asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x - 32) : "memory");  // all softmax warps are done
+        if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(&bars[3]) = 1;
+    }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
-template <int MODE, int OVH = 0>
+template <int MODE, int OVH = 0, int MMA = 0>
 void run(const char* name, float* out, float* in, long long* cyc) {
     printf("%-40s", name);
-    for (int wps = 1; wps <= MAXT / 128; ++wps) {
+    for (int wps = 1; wps <= 2; ++wps) {
         const int iters = 200;
-        k<MODE, OVH><<<1, wps * 128>>>(out, in, iters, cyc);
+        cudaFuncSetAttribute(k<MODE, OVH, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        k<MODE, OVH, MMA><<<1, wps * 128 + (MMA ? 32 : 0), 100 * 1024>>>(out, in, iters, cyc);
         cudaDeviceSynchronize();
-        k<MODE, OVH><<<1, wps * 128>>>(out, in, iters, cyc);
+        k<MODE, OVH, MMA><<<1, wps * 128 + (MMA ? 32 : 0), 100 * 1024>>>(out, in, iters, cyc);
         cudaDeviceSynchronize();
-        long long c;
-        cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+        long long c, c2[2];
+        cudaMemcpy(c2, cyc, 16, cudaMemcpyDeviceToHost);
+        c = c2[0];
+        if (MMA) printf(" [tensor busy %4.1f%%]", 100.0 * c2[1] * 2048.0 / (double)c);
         printf("  w/s %d: %7.1f per warp-tile, %7.1f per tile per scheduler |", wps, (double)c / iters, (double)c / iters / wps);
     }
     printf("\n");
@@ -194,7 +231,7 @@ int main() {
     long long* cyc;
     cudaMalloc(&out, 4096 * 4);
     cudaMalloc(&in, 4096 * 4);
-    cudaMalloc(&cyc, 8);
+    cudaMalloc(&cyc, 16);
     float h[4096];
     for (int i = 0; i < 4096; ++i) h[i] = -0.01f * (i % 977);
     h[1] = 0.127f;
@@ -210,6 +247,8 @@ int main() {
     run<0, 7>("full tile + arrivals + waits + tc fences", out, in, cyc);
     run<0, 15>("... + stats store", out, in, cyc);
     run<0, 31>("... + mask vote (all kernel hand-shakes)", out, in, cyc);
+    run<0, 0, 1>("full tile + tensor pipe busy (QK^T SS, PV TS)", out, in, cyc);
+    run<0, 31, 1>("all hand-shakes + tensor pipe busy", out, in, cyc);
     run<3>("max computed, exps independent of it", out, in, cyc);
     run<4>("2-input max, 8 chains", out, in, cyc);
     run<5>("3-input max, 8 chains", out, in, cyc);
