@@ -369,7 +369,15 @@ def bench_widened(dev):
         out["fwd_dropout0.1"] = rec(_time_events(lambda i: flash_attn_func(q, k, v, causal=True, dropout_p=0.1), 5), fl / 2)
     o = flash_attn_func(q, k, v, causal=True)
     out["bwd_causal"] = rec(_time_events(lambda i: torch.autograd.grad(o, (q, k, v), do, retain_graph=True), 10), 2.5 * fl / 2)
-    return {"workload": "config-2 shape (bf16 B=8 H=32 S=4096 D=128): non-causal forward, feature variants, backward", **out}
+    del q, k, v, o, do
+    # the other head dims at the same token count and model width (H * D = 4096): bf16 causal forward
+    with torch.no_grad():
+        for d in (64, 256):
+            h = 4096 // d
+            qd, kd, vd = (torch.randn(B, S, h, d, device=dev, dtype=torch.bfloat16) for _ in range(3))
+            out[f"fwd_causal_d{d}"] = rec(_time_events(lambda i: flash_attn_func(qd, kd, vd, causal=True), 10), 4.0 * d * B * h * S * S / 2)
+    return {"workload": "config-2 shape (bf16 B=8 H=32 S=4096 D=128): non-causal forward, feature variants, backward; "
+                        "head_dim 64 (H=64) and 256 (H=16) causal forward", **out}
 
 
 def bench_c4(dev, B, Hk=8):

@@ -27,10 +27,13 @@
 // both stages in turn and Q K^T(j+1) of a stage never waits for that stage's softmax(j) -> P V(j) (see FwdConfig).
 // FA_SHARED_S = 0 (round 1, kept for A/B): S0 [0,128) S1 [128,256), P_s aliases columns [64,128) of S_s.
 //
-// head_dim 256 ("split-D"): an O accumulator of 256 columns per query tile leaves no room for two stages, so
-// the two stages work on the SAME 128 query rows and each owns one 128-column half of O (stage s multiplies P
-// by V[:, 128 s .. 128 s + 128)). Both compute S = Q K^T over all 256 dims and the same softmax; Q, K and V are
-// loaded once per tile and shared. A work item is then one 128-row query block, and the TMEM map is unchanged.
+// head_dim 256: an O accumulator of 256 columns per query tile leaves no room for two stages of different rows, so a
+// work item is ONE 128-row query block and stage 0 runs alone: one S = Q K^T over all 256 dims, one softmax, one P V
+// with N = 256 into O0|O1 (contiguous columns); the Q K^T of tile j+1 runs under the softmax of tile j as at head_dim
+// 128 (shared S, private P). Stage 1's warps only take part in the work hand-out. K+V are 128 KB per tile, i.e.
+// 64 B/clk per SM at full tensor rate against ~42 B/clk of L2 -> SM throughput per SM: L2-bound at ~2/3 of the pipe.
+// FA_SPLIT_SINGLE = 0 (round 1, "split-D", kept for A/B): both stages work on the same rows, each computes S and
+// the softmax again and owns one 128-column half of O (stage s multiplies P by V[:, 128 s .. 128 s + 128)).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -136,6 +139,9 @@ constexpr float kNegSentinel = -1e30f;  // reference NEG_INF (include/kernel.h:2
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; O is rescaled only when the max moves more
 
 // Tuning knobs (compile-time; csrc/build.sh can override them with -D for A/B runs on the GPU).
+#ifndef FA_SPLIT_SINGLE
+#define FA_SPLIT_SINGLE 1  // head_dim 256: one Q K^T and one softmax per tile, one N=256 P V (0: round-1 split-D, both stages)
+#endif
 #ifndef FA_EMU_PERIOD
 #define FA_EMU_PERIOD 4  // of every FA_EMU_PERIOD pairs of exponentials ...
 #endif
@@ -364,7 +370,9 @@ FA_DEVICE WorkGeom finish_geom(const FwdKernelParams& p, const WorkHead& h) {
     for (int s = 0; s < 2; ++s) {
         const int r0 = w.m0 + (SPLIT ? 0 : s * BM);
         int hi_n = n_max, lo_n = n_min;
-        if (DECODE) {
+        if (SPLIT && FA_SPLIT_SINGLE && s == 1) {
+            hi_n = lo_n = n_min;  // head_dim 256: stage 0 alone (its P V covers all 256 output columns)
+        } else if (DECODE) {
             if (s == 1 && !SPLIT) hi_n = lo_n = n_min;  // single tile of packed rows: stage 1 is idle
         } else if (r0 >= w.g.seqlen_q) {
             hi_n = lo_n = n_min;  // no valid row in this stage
@@ -653,7 +661,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         reg_dec<48>();
         constexpr uint32_t idesc_qk = umma_idesc_f16(BF16, BM, BN, false, false);
         constexpr uint32_t idesc_qk_half = umma_idesc_f16(BF16, BM, BN / 2, false, false);
-        constexpr uint32_t idesc_pv = umma_idesc_f16(BF16, BM, DO, false, true);
+        constexpr bool SPLIT1 = SPLIT && FA_SPLIT_SINGLE;  // one stage, P V with N = 256 into O0|O1 (contiguous columns)
+        constexpr uint32_t idesc_pv = umma_idesc_f16(BF16, BM, SPLIT1 ? 2 * DO : DO, false, true);
         const uint32_t tS[2] = {tmem_base + Cfg::kTmemS0, tmem_base + Cfg::kTmemS1};
         const uint32_t tO[2] = {tmem_base + Cfg::kTmemO0, tmem_base + Cfg::kTmemO1};
         // Descriptor words (ptx_sm100.cuh): lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version | swizzle.
@@ -746,7 +755,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         const uint32_t ph = (steps[s] + j) & 1;
                         const uint32_t tP = tPs[s];
                         // split-D: stage s multiplies by its own 128-column half of V (two swizzle blocks further)
-                        const uint32_t v_lo = lo_addr(slot_addr(ring + 2 * it - 1) + (SPLIT ? s * 2 * Cfg::kHalfBytes : 0)) | kLoVmn;
+                        const uint32_t v_lo = lo_addr(slot_addr(ring + 2 * it - 1) + (SPLIT && !SPLIT1 ? s * 2 * Cfg::kHalfBytes : 0)) | kLoVmn;
                         if (Cfg::kEarlyQK) {
                             // S_s(j) sits in the softmax warps' registers: columns [0,64) of S_s are free, so the left
                             // half of the next S_s can be computed while P_s(j) is still being made
@@ -1068,6 +1077,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tO[2] = {tmem_base + lane_off + Cfg::kTmemO0, tmem_base + lane_off + Cfg::kTmemO1};
+        constexpr bool SPLIT1 = SPLIT && FA_SPLIT_SINGLE;
+        constexpr int kStageCols = SPLIT1 ? 2 * DO : DO;  // O columns one stage accumulates (head_dim 256, single stage: O0|O1)
         uint16_t* outp = reinterpret_cast<uint16_t*>(p.out);
         int steps[2] = {0, 0};
         int items[2] = {0, 0};
@@ -1123,7 +1134,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         if (p.dbg_counters && lane == 0) atomicAdd(p.dbg_counters + 1, 1ull);
                         tc_fence_after();
 #pragma unroll
-                        for (int c = 0; c < DO / 32; ++c) {
+                        for (int c = 0; c < kStageCols / 32; ++c) {
                             float o[32];
                             tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
 #pragma unroll
@@ -1141,10 +1152,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 if (DECODE && !SPLIT && s == 1) continue;  // packed-row mode has a single tile
+                if (SPLIT1 && s == 1) continue;             // stage 0 writes all 256 columns
                 const int i_glob = DECODE ? row / G : w.m0 + (SPLIT ? 0 : s * BM) + row;
                 const int h_row = DECODE ? w.head + row % G : w.head;
                 const bool valid = i_glob < w.g.seqlen_q;
-                constexpr int kColStep = SPLIT ? DO : 0;  // split-D: stage s owns output columns [s*128, s*128+128)
+                constexpr int kColStep = (SPLIT && !SPLIT1) ? DO : 0;  // two-stage split-D: stage s owns output columns [s*128, s*128+128)
                 const int col0 = s * kColStep;
                 const bool own_lse = !(SPLIT && s == 1);
                 uint16_t* dst = outp + w.o_b * p.o_stride_b + (int64_t)(w.g.q_off + i_glob) * p.o_stride_s +
@@ -1153,7 +1165,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 if (w.it_hi[s] <= w.it_lo[s]) {  // this stage saw no KV tile: no key is visible to its rows
                     if (valid) {
 #pragma unroll
-                        for (int c = 0; c < DO; c += 8)
+                        for (int c = 0; c < kStageCols; c += 8)
                             if (col0 + c < p.head_dim) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0, 0, 0, 0);
                         if (own_lse) *lse_dst = kNegSentinel;
                     }
@@ -1172,7 +1184,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     // split-KV partial: normalised fp32 O and this split's LSE; fa_combine_kernel merges them
                     const int64_t prow = (((int64_t)w.split * num_batch + w.batch) * p.num_heads + h_row) * w.g.seqlen_q + i_glob;
 #pragma unroll
-                    for (int c = 0; c < DO / 32; ++c) {
+                    for (int c = 0; c < kStageCols / 32; ++c) {
                         float o[32];
                         tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
                         if (valid) {
@@ -1185,7 +1197,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     if (valid && own_lse) p.lse_partial[prow] = l > 0.f ? (mx + lg2_approx(l)) * kLn2 : -INFINITY;
                 } else {
 #pragma unroll
-                    for (int c = 0; c < DO / 32; ++c) {
+                    for (int c = 0; c < kStageCols / 32; ++c) {
                         if (col0 + c * 32 >= p.head_dim) break;  // columns [head_dim, D) are the tile's zero padding
                         float o[32];
                         tmem_ld_x32_wait(tO[s] + c * 32, reinterpret_cast<uint32_t*>(o));
