@@ -46,6 +46,8 @@ WORKLOADS = {
                desc="bf16 B=8 H=32 Hk=32 S=4096 D=128 causal per GPU (BASELINE config 2, Llama-3-8B shape)"),
     "c2gqa": dict(batch=8, heads=32, heads_k=8, seqlen=4096, head_dim=128, causal=True, window=(-1, -1),
                   desc="bf16 B=8 H=32 Hk=8 S=4096 D=128 causal per GPU (config 2 with Llama-3-8B GQA)"),
+    "d256": dict(batch=8, heads=16, heads_k=16, seqlen=4096, head_dim=256, causal=True, window=(-1, -1),
+                 desc="bf16 B=8 H=16 Hk=16 S=4096 D=256 causal per GPU (SURVEY 8(f)-3: the 256-wide tile)"),
     "c5": dict(batch=64, heads=32, heads_k=32, seqlen=8192, head_dim=128, causal=True, window=(4096, 0), strong=True,
                desc="bf16 B=64 (global, sharded over the ranks) H=32 S=8192 D=128 causal + window 4096 (BASELINE config 5)"),
 }

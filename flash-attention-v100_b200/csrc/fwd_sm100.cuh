@@ -30,8 +30,10 @@
 // head_dim 256: an O accumulator of 256 columns per query tile leaves no room for two stages of different rows, so a
 // work item is ONE 128-row query block and stage 0 runs alone: one S = Q K^T over all 256 dims, one softmax, one P V
 // with N = 256 into O0|O1 (contiguous columns); the Q K^T of tile j+1 runs under the softmax of tile j as at head_dim
-// 128 (shared S, private P). Stage 1's warps only take part in the work hand-out. K+V are 128 KB per tile, i.e.
-// 64 B/clk per SM at full tensor rate against ~42 B/clk of L2 -> SM throughput per SM: L2-bound at ~2/3 of the pipe.
+// 128 (shared S, private P). Stage 1's warps only take part in the work hand-out. One 64 KB K tile and one V tile
+// fit beside Q, so they are handed over in 32 KB halves (FwdConfig::kHalfRing): Q K^T releases the first 128 dims of
+// K while it works on the second, P V is issued per 128 output columns, and the loader refills each half as it frees
+// up, K one tile ahead of V. K+V are 128 KB per tile: the SM's ingest rate, not the tensor pipe, bounds this path.
 // FA_SPLIT_SINGLE = 0 (round 1, "split-D", kept for A/B): both stages work on the same rows, each computes S and
 // the softmax again and owns one 128-column half of O (stage s multiplies P by V[:, 128 s .. 128 s + 128)).
 #pragma once
@@ -139,6 +141,9 @@ constexpr float kNegSentinel = -1e30f;  // reference NEG_INF (include/kernel.h:2
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; O is rescaled only when the max moves more
 
 // Tuning knobs (compile-time; csrc/build.sh can override them with -D for A/B runs on the GPU).
+#ifndef FA_HALF_RING
+#define FA_HALF_RING 1  // head_dim 256 single stage: K / V tiles handed over in 32 KB halves (0: whole 64 KB tiles)
+#endif
 #ifndef FA_SPLIT_SINGLE
 #define FA_SPLIT_SINGLE 1  // head_dim 256: one Q K^T and one softmax per tile, one N=256 P V (0: round-1 split-D, both stages)
 #endif
@@ -192,9 +197,16 @@ struct FwdConfig {
     static constexpr bool kSplitD = (D == 256);            // see "split-D" in the header comment
     static constexpr int kDO = kSplitD ? 128 : D;          // columns of one stage's O accumulator
     static constexpr int kItemRows = kSplitD ? kBlockM : 2 * kBlockM;  // query rows of one work item
-    static constexpr int kKvStages = (D == 256) ? 2 : (D == 128) ? 4 : 6;
+    // head_dim 256, single stage: the K and V tiles (64 KB each, one of each fits) are handed over in halves of two
+    // swizzle blocks (head dims [0,128) and [128,256)): Q K^T runs over the first half of the dims and releases it while it
+    // works on the second, P V is issued per 128 output columns -- so the next tile's loads start half a GEMM earlier and
+    // the ring has four 32 KB slots K-lo K-hi V-lo V-hi instead of two of 64 KB (same bytes, same layout in memory).
+    static constexpr bool kHalfRing = kSplitD && FA_SPLIT_SINGLE && FA_HALF_RING;
+    static constexpr int kKvStages = (D == 256) ? (kHalfRing ? 4 : 2) : (D == 128) ? 4 : 6;
+    static constexpr int kSlotBytes = kHalfRing ? kTileBytes / 2 : kTileBytes;
+    static constexpr int kEntriesPerTile = kHalfRing ? 4 : 2;  // ring entries of one KV tile
     static constexpr int kSmemQ = kSplitD ? kTileBytes : 2 * kTileBytes;
-    static constexpr int kSmemKV = kKvStages * kTileBytes;
+    static constexpr int kSmemKV = kKvStages * kSlotBytes;
     static constexpr int kNumBars = 2 + 2 * kKvStages + 6 * 2 + 1 + 2 + 4 + 1 + 2 + 1 + 1 + 2 + 2;
     static constexpr int kOffBars = kSmemQ + kSmemKV;
     static constexpr int kOffTmemPtr = kOffBars + 8 * kNumBars;
@@ -620,22 +632,36 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         row = w.g.k_off + r;
                     }
                 };
-                auto produce = [&](const CUtensorMap* tm, int n) {
-                    const int slot = ring % KV;
-                    const uint32_t parity = ((ring / KV) & 1) ^ 1;
-                    mbar_wait(bar_kv_empty(slot), parity);
-                    FA_TRACE_EV(310);  // loader: ring slot free
-                    if (lane == 0) {
-                        int row, b;
-                        kv_coords(n, row, b);
-                        load_tile(tm, sKV + slot * Cfg::kTileBytes, bar_kv_full(slot), w.kv_head, row, b);
+                constexpr int EPT = Cfg::kEntriesPerTile;
+                const int base = ring;  // tile `it` of the item: K = ring entries base + EPT*it .., V = base + EPT*it + EPT/2 ..
+                auto produce = [&](const CUtensorMap* tm, int n, int entry) {
+                    int row = 0, b = 0;
+                    if (lane == 0) kv_coords(n, row, b);
+#pragma unroll
+                    for (int half = 0; half < (Cfg::kHalfRing ? 2 : 1); ++half) {
+                        const int slot = (entry + half) % KV;
+                        const uint32_t parity = (((entry + half) / KV) & 1) ^ 1;
+                        mbar_wait(bar_kv_empty(slot), parity);
+                        FA_TRACE_EV(310);  // loader: ring slot free
+                        if (lane == 0) {
+                            const uint32_t dst = sKV + slot * Cfg::kSlotBytes, bar = bar_kv_full(slot);
+                            if (Cfg::kHalfRing) {  // two of the tile's four 64-column blocks
+                                mbar_arrive_expect_tx(bar, Cfg::kSlotBytes);
+#pragma unroll
+                                for (int c = 0; c < 2; ++c)
+                                    tma_load_4d(dst + c * Cfg::kHalfBytes, tm, bar, (half * 2 + c) * 64, w.kv_head, row, b);
+                            } else {
+                                load_tile(tm, dst, bar, w.kv_head, row, b);
+                            }
+                        }
                     }
-                    ++ring;
                 };
+                auto k_entry = [&](int it) { return base + EPT * it; };
+                auto v_entry = [&](int it) { return base + EPT * it + EPT / 2; };
                 // The first K tile only needs a ring slot (free long before the previous item ends): it goes out first, so that
                 // at the item boundary only the Q tiles are still to come (an SM takes in ~40-60 B/clk: Q + K + V of a first
                 // iteration are 128 KB = ~2800 clocks after the Q buffer frees up, measured; Q alone is half of that).
-                produce(&p.tm_k, w.n_max - 1);
+                produce(&p.tm_k, w.n_max - 1, k_entry(0));
                 // Q tiles of the previous item must have been consumed by its last QK^T
                 FA_TRACE_EV(300);  // loader: waiting for the Q buffer
                 mbar_wait(bar_q_empty, (ka & 1) ^ 1);
@@ -644,12 +670,26 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 if (lane == 0) load_tile(&p.tm_q, sQ, bar_q_full(0), w.head, w.g.q_off + w.m0, w.g.q_b);
                 if (!DECODE && !SPLIT && lane == 0)
                     load_tile(&p.tm_q, sQ + Cfg::kTileBytes, bar_q_full(1), w.head, w.g.q_off + w.m0 + BM, w.g.q_b);
-                produce(&p.tm_v, w.n_max - 1);
-                FA_TRACE_EV(302);  // loader: Q0, K, Q1, V of the first iteration issued
-                for (int it = 1; it < w.n_tiles; ++it) {
-                    produce(&p.tm_k, w.n_max - 1 - it);
-                    produce(&p.tm_v, w.n_max - 1 - it);
+                if (Cfg::kHalfRing) {
+                    // One K and one V tile fit: K goes one tile ahead of V, K(0) | Q | V(0) K(1) | K(2) V(1) | K(3) V(2) .. --
+                    // the order in which the MMA warp frees the slots (Q K^T(it+1) is issued before P V(it)); with K(it+1)
+                    // behind V(it) in this in-order queue it would wait a whole P V longer than its slot does. (V(0)'s slots
+                    // are free once the previous item's last P V is done, long before Q K^T(0) frees K(1)'s.)
+                    produce(&p.tm_v, w.n_max - 1, v_entry(0));
+                    FA_TRACE_EV(302);  // loader: the first iteration's tiles are on their way
+                    for (int it = 0; it < w.n_tiles; ++it) {
+                        if (it + 1 < w.n_tiles) produce(&p.tm_k, w.n_max - 2 - it, k_entry(it + 1));
+                        if (it > 0) produce(&p.tm_v, w.n_max - 1 - it, v_entry(it));
+                    }
+                } else {
+                    produce(&p.tm_v, w.n_max - 1, v_entry(0));
+                    FA_TRACE_EV(302);  // loader: Q0, K, Q1, V of the first iteration issued
+                    for (int it = 1; it < w.n_tiles; ++it) {
+                        produce(&p.tm_k, w.n_max - 1 - it, k_entry(it));
+                        produce(&p.tm_v, w.n_max - 1 - it, v_entry(it));
+                    }
                 }
+                ring = base + EPT * w.n_tiles;
                 ++ka;
             }
             id = prefetching ? fetch_read() : total_work;
@@ -663,6 +703,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         constexpr uint32_t idesc_qk_half = umma_idesc_f16(BF16, BM, BN / 2, false, false);
         constexpr bool SPLIT1 = SPLIT && FA_SPLIT_SINGLE;  // one stage, P V with N = 256 into O0|O1 (contiguous columns)
         constexpr uint32_t idesc_pv = umma_idesc_f16(BF16, BM, SPLIT1 ? 2 * DO : DO, false, true);
+        constexpr uint32_t idesc_pv_half = umma_idesc_f16(BF16, BM, DO, false, true);  // half ring: 128 output columns at a time
         const uint32_t tS[2] = {tmem_base + Cfg::kTmemS0, tmem_base + Cfg::kTmemS1};
         const uint32_t tO[2] = {tmem_base + Cfg::kTmemO0, tmem_base + Cfg::kTmemO1};
         // Descriptor words (ptx_sm100.cuh): lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version | swizzle.
@@ -690,7 +731,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             else if constexpr (D == 128) umma_issue_qk_d128(d, a_lo, b_lo, kDescHi, kDescHi, idesc_qk_half);
             else umma_issue_qk_d64(d, a_lo, b_lo, kDescHi, kDescHi, idesc_qk_half);
         };
-        auto slot_addr = [&](int r) { return sKV + (r % KV) * Cfg::kTileBytes; };
+        // head_dim 256, half ring: dims [128 h, 128 h + 128) of S = Q K^T (two swizzle blocks of Q and the K half-slot)
+        auto issue_qk_dims = [&](uint32_t k_smem, int h) {
+            const uint32_t a_lo = lo_addr(sQ + h * 2 * Cfg::kHalfBytes) | kLoKmajor;
+            const uint32_t b_lo = lo_addr(k_smem) | kLoKmajor;
+            umma_issue_qk_half256(tS[0], a_lo, b_lo, kDescHi, kDescHi, idesc_qk, h ? 1u : 0u);
+        };
+        auto slot_addr = [&](int r) { return sKV + (r % KV) * Cfg::kSlotBytes; };
+        constexpr int EPT = Cfg::kEntriesPerTile;  // ring entries per KV tile: K, V -- or K-lo, K-hi, V-lo, V-hi
         auto wait_full = [&](int r) { mbar_wait(bar_kv_full(r % KV), (r / KV) & 1); };
 
         const uint32_t tPs[2] = {tmem_base + Cfg::kTmemP0, tmem_base + Cfg::kTmemP1};
@@ -718,7 +766,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             // rule) has been copied to registers, so it runs while its own stage is still busy with the tile before.
             // Either way the first QK^T of the next item may follow the last P V of this one directly.
             for (int it = 0; it <= w.n_tiles; ++it) {
-                if (it < w.n_tiles) wait_full(ring + 2 * it);
+                if (!Cfg::kHalfRing && it < w.n_tiles) wait_full(ring + EPT * it);  // (half ring: each half right before its MMAs)
                 bool v_ready = false;  // V(it-1) is only waited for by the first P V of the iteration (a Q K^T does not need it)
                 if (!DECODE && !SPLIT && it == 0) mbar_wait(bar_q_full(1), ka & 1);
                 const bool qk0_this_it = it < w.n_tiles && it >= w.it_lo[0] && it < w.it_hi[0];
@@ -733,19 +781,57 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                             ++sx_uses;
                         }
                         tc_fence_after();
-                        if (Cfg::kEarlyQK && do_pv) issue_qk_half(s, slot_addr(ring + 2 * it), 1);  // left half went ahead
-                        else issue_qk(s, slot_addr(ring + 2 * it));
+                        if (Cfg::kHalfRing) {
+                            // the first half of the dims, its K half-slot released right behind it, then the second half
+                            wait_full(ring + EPT * it);
+                            tc_fence_after();
+                            issue_qk_dims(slot_addr(ring + EPT * it), 0);
+                            umma_commit_elect(bar_kv_empty((ring + EPT * it) % KV));
+                            wait_full(ring + EPT * it + 1);
+                            tc_fence_after();
+                            issue_qk_dims(slot_addr(ring + EPT * it + 1), 1);
+                            umma_commit_elect(bar_kv_empty((ring + EPT * it + 1) % KV));
+                        } else if (Cfg::kEarlyQK && do_pv) {
+                            issue_qk_half(s, slot_addr(ring + EPT * it), 1);  // left half went ahead
+                        } else {
+                            issue_qk(s, slot_addr(ring + EPT * it));
+                        }
                         umma_commit_elect(bar_s_full(s));
                         // the item's last Q K^T: the Q buffer is free as soon as it completes (a commit at the end of the
                         // iteration would also wait for the P V issued behind it, i.e. for a whole softmax)
                         if (it == last_qk_it && s == last_qk_s) umma_commit_elect(bar_q_empty);
                         // likewise the K tile: free once the iteration's last Q K^T has read it (shared-S order only: there
                         // a P V of the previous iteration is issued BEHIND this Q K^T and would hold the slot for a softmax)
-                        if (Cfg::kSharedS && (s == 1 || !qk1_this_it)) umma_commit_elect(bar_kv_empty((ring + 2 * it) % KV));
+                        if (!Cfg::kHalfRing && Cfg::kSharedS && (s == 1 || !qk1_this_it)) umma_commit_elect(bar_kv_empty((ring + EPT * it) % KV));
                         FA_TRACE_EV(120 + s);  // MMA: QK_s issued
                     };
                     if (Cfg::kSharedS && do_qk) qk();
-                    if (do_pv) {
+                    if (Cfg::kHalfRing && do_pv) {
+                        // head_dim 256, half ring (stage 0 alone): O0 += P V[:, 0:128) from the V-lo slot, released right behind
+                        // it, then O1 += P V[:, 128:256) from the V-hi slot
+                        const int ve = ring + EPT * (it - 1) + 2;
+                        wait_full(ve);
+                        if (it == 1 && w.ragged_tail) mbar_wait(bar_vfix, kfix & 1);  // V rows past seqlen_k are zero now
+                        const int j = it - 1 - w.it_lo[s];
+                        const uint32_t ph = (steps[s] + j) & 1;
+                        const uint32_t acc = j > 0 ? 1u : 0u;
+                        const uint32_t v0 = lo_addr(slot_addr(ve)) | kLoVmn, v1 = lo_addr(slot_addr(ve + 1)) | kLoVmn;
+                        mbar_wait(bar_p_full(s), ph);
+                        tc_fence_after();
+                        FA_TRACE_EV(100 + s);  // MMA: P_s (3/4) + O rescale observed
+                        umma_issue_pv_k0_6(tO[0], tPs[s], v0, 0, kDescHi, idesc_pv_half, acc);
+                        mbar_wait(bar_p_last(s), ph);
+                        tc_fence_after();
+                        FA_TRACE_EV(110 + s);  // MMA: last quarter of P_s observed
+                        umma_issue_pv_k6_8(tO[0], tPs[s], v0, 0, kDescHi, idesc_pv_half, 1u);
+                        umma_commit_elect(bar_kv_empty(ve % KV));
+                        wait_full(ve + 1);
+                        tc_fence_after();
+                        umma_issue_pv_k0_8(tO[1], tPs[s], v1, 0, kDescHi, idesc_pv_half, acc);
+                        umma_commit_elect(bar_kv_empty((ve + 1) % KV));
+                        umma_commit_elect(bar_p_free(s));  // P_s may be overwritten, O_s rescaled
+                        if (it == w.it_hi[s]) umma_commit_elect(bar_o_full(s));
+                    } else if (do_pv) {
                         if (!v_ready) {
                             wait_full(ring + 2 * it - 1);
                             if (it == 1 && w.ragged_tail) mbar_wait(bar_vfix, kfix & 1);  // V rows past seqlen_k are zero now
@@ -784,13 +870,31 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                     }
                     if (!Cfg::kSharedS && do_qk) qk();
                 }
-                if (it > 0) umma_commit_elect(bar_kv_empty((ring + 2 * it - 1) % KV));
-                if (it < w.n_tiles && !(Cfg::kSharedS && (qk0_this_it || qk1_this_it))) umma_commit_elect(bar_kv_empty((ring + 2 * it) % KV));
+                if (Cfg::kHalfRing) {
+                    // (every tile of a head_dim-256 item is used by stage 0, which releases the half-slots itself; a tile
+                    // nobody multiplies with would still have to land before its slots go back to the loader)
+                    if (it < w.n_tiles && !qk0_this_it) {
+                        wait_full(ring + EPT * it);
+                        wait_full(ring + EPT * it + 1);
+                        umma_commit_elect(bar_kv_empty((ring + EPT * it) % KV));
+                        umma_commit_elect(bar_kv_empty((ring + EPT * it + 1) % KV));
+                    }
+                    const bool pv0_this_it = it > 0 && (it - 1) >= w.it_lo[0] && (it - 1) < w.it_hi[0];
+                    if (it > 0 && !pv0_this_it) {
+                        wait_full(ring + EPT * (it - 1) + 2);
+                        wait_full(ring + EPT * (it - 1) + 3);
+                        umma_commit_elect(bar_kv_empty((ring + EPT * (it - 1) + 2) % KV));
+                        umma_commit_elect(bar_kv_empty((ring + EPT * (it - 1) + 3) % KV));
+                    }
+                } else {
+                    if (it > 0) umma_commit_elect(bar_kv_empty((ring + 2 * it - 1) % KV));
+                    if (it < w.n_tiles && !(Cfg::kSharedS && (qk0_this_it || qk1_this_it))) umma_commit_elect(bar_kv_empty((ring + 2 * it) % KV));
+                }
                 // (bar_q_empty is committed right behind the item's last Q K^T, see qk(); an item none of whose stages has a
                 // tile -- possible with Sq > Sk and a window -- releases the Q buffer here)
                 if (last_qk_it < 0 && it == w.n_tiles - 1) umma_commit_elect(bar_q_empty);
             }
-            ring += 2 * w.n_tiles;
+            ring += EPT * w.n_tiles;
             steps[0] += w.it_hi[0] - w.it_lo[0];
             steps[1] += w.it_hi[1] - w.it_lo[1];
             kfix += w.ragged_tail ? 1 : 0;
@@ -1239,10 +1343,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             const WorkGeom w = finish_geom<DECODE, SPLIT>(p, wk.h);
             if (w.n_tiles <= 0) continue;
             if (w.ragged_tail) {
-                const int v_entry = ring + 1;
+                const int v_entry = ring + Cfg::kEntriesPerTile / 2;
+                if (Cfg::kHalfRing) mbar_wait(bar_kv_full((v_entry + 1) % KV), ((v_entry + 1) / KV) & 1);  // both halves of V
                 const int valid = w.g.seqlen_k - (w.n_max - 1) * BN;  // rows of the tail tile that hold keys
                 mbar_wait(bar_kv_full(v_entry % KV), (v_entry / KV) & 1);
-                const uint32_t v_smem = sKV + (v_entry % KV) * Cfg::kTileBytes;
+                const uint32_t v_smem = sKV + (v_entry % KV) * Cfg::kSlotBytes;  // (half ring: V-lo | V-hi are adjacent)
                 // rows are 128 B long inside each 64-column block; the swizzle only permutes 16 B chunks in a row
                 for (int idx = lane; idx < (BN - valid) * 8 * (D / 64); idx += 32) {
                     const int c16 = idx & 7, r = valid + ((idx >> 3) % (BN - valid)), blk = (idx >> 3) / (BN - valid);
@@ -1252,7 +1357,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_vfix);
             }
-            ring += 2 * w.n_tiles;
+            ring += Cfg::kEntriesPerTile * w.n_tiles;
         }
         watchdog_role_done(bar_done);
     } else {
