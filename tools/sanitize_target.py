@@ -13,7 +13,7 @@ from flash_attn_v100 import flash_attn_func, flash_attn_varlen_func, flash_attn_
 
 torch.manual_seed(0)
 dt = torch.bfloat16
-for D in (40, 128, 256):
+for D in (40, 128, 192, 256):
     q = torch.randn(1, 77, 2, D, device="cuda", dtype=dt, requires_grad=True)
     k = torch.randn(1, 203, 1, D, device="cuda", dtype=dt, requires_grad=True)
     v = torch.randn(1, 203, 1, D, device="cuda", dtype=dt, requires_grad=True)
