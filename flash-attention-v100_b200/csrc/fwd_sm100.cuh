@@ -646,9 +646,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         if (lane == 0) {
                             const uint32_t dst = sKV + slot * Cfg::kSlotBytes, bar = bar_kv_full(slot);
                             if (Cfg::kHalfRing) {  // two of the tile's four 64-column blocks
-                                mbar_arrive_expect_tx(bar, Cfg::kSlotBytes);
-#pragma unroll
-                                for (int c = 0; c < 2; ++c)
+                                // (head_dim <= 192: the fourth block would be all padding -- it is neither loaded nor read)
+                                const int blocks = (half == 1 && p.head_dim <= 192) ? 1 : 2;
+                                mbar_arrive_expect_tx(bar, blocks * Cfg::kHalfBytes);
+                                for (int c = 0; c < blocks; ++c)
                                     tma_load_4d(dst + c * Cfg::kHalfBytes, tm, bar, (half * 2 + c) * 64, w.kv_head, row, b);
                             } else {
                                 load_tile(tm, dst, bar, w.kv_head, row, b);
@@ -704,6 +705,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
         constexpr bool SPLIT1 = SPLIT && FA_SPLIT_SINGLE;  // one stage, P V with N = 256 into O0|O1 (contiguous columns)
         constexpr uint32_t idesc_pv = umma_idesc_f16(BF16, BM, SPLIT1 ? 2 * DO : DO, false, true);
         constexpr uint32_t idesc_pv_half = umma_idesc_f16(BF16, BM, DO, false, true);  // half ring: 128 output columns at a time
+        constexpr uint32_t idesc_pv_quarter = umma_idesc_f16(BF16, BM, 64, false, true);  // head_dim <= 192: columns [128,192)
         const uint32_t tS[2] = {tmem_base + Cfg::kTmemS0, tmem_base + Cfg::kTmemS1};
         const uint32_t tO[2] = {tmem_base + Cfg::kTmemO0, tmem_base + Cfg::kTmemO1};
         // Descriptor words (ptx_sm100.cuh): lo = addr>>4 | (LBO>>4)<<16, hi = SBO>>4 | version | swizzle.
@@ -732,10 +734,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
             else umma_issue_qk_d64(d, a_lo, b_lo, kDescHi, kDescHi, idesc_qk_half);
         };
         // head_dim 256, half ring: dims [128 h, 128 h + 128) of S = Q K^T (two swizzle blocks of Q and the K half-slot)
+        const bool narrow = Cfg::kHalfRing && p.head_dim <= 192;  // dims [192,256) are padding: skip their MMAs
         auto issue_qk_dims = [&](uint32_t k_smem, int h) {
             const uint32_t a_lo = lo_addr(sQ + h * 2 * Cfg::kHalfBytes) | kLoKmajor;
             const uint32_t b_lo = lo_addr(k_smem) | kLoKmajor;
-            umma_issue_qk_half256(tS[0], a_lo, b_lo, kDescHi, kDescHi, idesc_qk, h ? 1u : 0u);
+            if (h == 1 && narrow) umma_issue_qk_quarter256(tS[0], a_lo, b_lo, kDescHi, kDescHi, idesc_qk, 1u);
+            else umma_issue_qk_half256(tS[0], a_lo, b_lo, kDescHi, kDescHi, idesc_qk, h ? 1u : 0u);
         };
         auto slot_addr = [&](int r) { return sKV + (r % KV) * Cfg::kSlotBytes; };
         constexpr int EPT = Cfg::kEntriesPerTile;  // ring entries per KV tile: K, V -- or K-lo, K-hi, V-lo, V-hi
@@ -827,7 +831,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ FwdKernelParams p) {
                         umma_commit_elect(bar_kv_empty(ve % KV));
                         wait_full(ve + 1);
                         tc_fence_after();
-                        umma_issue_pv_k0_8(tO[1], tPs[s], v1, 0, kDescHi, idesc_pv_half, acc);
+                        umma_issue_pv_k0_8(tO[1], tPs[s], v1, 0, kDescHi, narrow ? idesc_pv_quarter : idesc_pv_half, acc);
                         umma_commit_elect(bar_kv_empty((ve + 1) % KV));
                         umma_commit_elect(bar_p_free(s));  // P_s may be overwritten, O_s rescaled
                         if (it == w.it_hi[s]) umma_commit_elect(bar_o_full(s));

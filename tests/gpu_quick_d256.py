@@ -91,11 +91,17 @@ if __name__ == "__main__":
                 parity("d256_alibi_softcap", 1, 777, 777, 4, 4, 256, bf16, True, softcap=30.0, alibi=True),
                 parity("d256_sq1_sk4000", 2, 1, 4000, 8, 2, 256, bf16, True),
                 parity("d256_many_items", 2, 2048, 2048, 40, 8, 256, bf16, True),
+                parity("d136_causal_700", 1, 700, 700, 2, 2, 136, bf16, True),
+                parity("d192_ragged_333x777_gqa", 2, 333, 777, 4, 2, 192, f16, True),
+                parity("d184_window_softcap", 1, 900, 900, 2, 1, 184, bf16, True, window=(200, 0), softcap=20.0),
+                parity_decode("d192_decode_B3_3000", 3, 3000, 8, 2, 192),
                 parity_decode("d256_decode_B4_8192", 4, 8192, 16, 4, 256),
                 parity_decode("d256_decode_B1_1000", 1, 1000, 8, 8, 256)]
     res += [bench("D256_bf16_B8_H16_S4096_causal", 8, 4096, 16, 16, 256, bf16, True),
             bench("D256_bf16_B8_H16_S4096_full", 8, 4096, 16, 16, 256, bf16, False),
             bench("D192_bf16_B8_H16_S4096_causal", 8, 4096, 16, 16, 192, bf16, True),
+            bench("D192_bf16_B8_H16_S4096_full", 8, 4096, 16, 16, 192, bf16, False),
+            bench("D160_bf16_B8_H16_S4096_causal", 8, 4096, 16, 16, 160, bf16, True),
             bench("D256_bf16_B32_H16_S1024_causal", 32, 1024, 16, 16, 256, bf16, True, iters=50)]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"quick_d256_{tag}.json"), "w"), indent=1)
