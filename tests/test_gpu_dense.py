@@ -123,6 +123,15 @@ def test_head_dims_any_multiple_of_8(api, D):
     check_dense(out, None, q, k, v, causal=True)
 
 
+@pytest.mark.parametrize("D,causal", [(136, True), (160, False), (184, True), (192, True), (200, False), (256, True)])
+def test_wide_tile_head_dims_many_tiles(api, D, causal):
+    """Head dims 129..256 share the 256-wide tile (one stage, K/V handed over in halves); up to 192 the tile's fourth
+    64-column block is all padding and is neither loaded nor multiplied. Several tiles per item, several items, GQA."""
+    q, k, v = rand_qkv(2, 700, 1100, 6, 2, D, torch.bfloat16)
+    out = api.flash_attn_func(q, k, v, causal=causal)
+    check_dense(out, None, q, k, v, causal=causal)
+
+
 def test_lse_and_return_conventions(api, op):
     q, k, v = rand_qkv(2, 300, 300, 4, 4, 128, torch.bfloat16)
     # dense return_attn_probs=True with dropout_p=0 raises, like the reference (fused_mha_forward.cu:371)
