@@ -42,6 +42,8 @@ dense("ragged_sq_ne_sk", 2, 333, 777, 4, 2, 128, True)
 dense("window", 1, 1536, 1536, 8, 8, 128, True, window=(300, 0))
 dense("d64", 2, 1024, 1024, 16, 16, 64, True, dt=torch.float16)
 dense("d256", 1, 1024, 1024, 8, 8, 256, True)
+dense("d256_full_many_items", 2, 1536, 1536, 24, 6, 256, False, reps=2)
+dense("d192", 1, 1024, 1024, 8, 8, 192, True)
 lens = [5, 333, 128, 1, 640, 257, 1900, 77]
 cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
 T = sum(lens)
